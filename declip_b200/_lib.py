@@ -1,0 +1,143 @@
+"""ctypes binding of declip_b200/_C.so (the C ABI declared in include/declip_b200.h).
+
+There is NO fallback: if the shared library is missing, or the device is not an sm_100a part,
+every entry point raises.  Nothing under `oracle/` is ever imported from here.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_C.so")
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+_missing = []
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_size_t = ctypes.c_size_t
+c_ll = ctypes.c_longlong
+c_ull = ctypes.c_ulonglong
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_int), ("a_mn_major", c_int),
+        ("B", c_void_p), ("ldb", c_int), ("b_mn_major", c_int),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("epilogue", c_int), ("alpha", c_float),
+        ("out", c_void_p), ("ldo", c_int),
+        ("out2", c_void_p), ("ldo2", c_int),
+        ("bias", c_void_p),
+        ("aux", c_void_p), ("ldaux", c_int),
+        ("splits", c_int), ("block_n", c_int),
+    ]
+
+
+class TowerCfg(ctypes.Structure):
+    _fields_ = [
+        ("layers", c_int), ("width", c_int), ("heads", c_int), ("seq_len", c_int), ("causal", c_int),
+        ("batch", c_int), ("embed_dim", c_int), ("res", c_int), ("patch", c_int), ("vocab", c_int),
+    ]
+
+
+class CastEntry(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("numel", c_ull)]
+
+
+# name -> (restype, argtypes); every symbol include/declip_b200.h declares.
+SIGNATURES = {
+    "dc_version": (c_int, []),
+    "dc_last_error": (ctypes.c_char_p, []),
+    "dc_init": (c_int, [c_int]),
+    "dc_sm_count": (c_int, []),
+    "dc_launch_count": (c_ll, []),
+    "dc_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "dc_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                 c_void_p]),
+    "dc_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_int, c_void_p]),
+    "dc_colsum_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dc_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "dc_multi_cast_f32_bf16": (c_int, [c_void_p, c_int, c_ull, c_void_p]),
+    "dc_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dc_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                 c_void_p]),
+    "dc_patchify": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dc_vit_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dc_text_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dc_text_embed_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "dc_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dc_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dc_eot_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dc_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "dc_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "dc_ce_strip": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_int, c_void_p, c_void_p]),
+    "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
+    "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "dc_vit_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "dc_text_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "dc_text_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
+}
+
+
+def so_path():
+    return _SO
+
+
+def load():
+    """dlopen the library and attach the signatures.  Does not touch the GPU."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                "declip_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback." % _SO)
+        lib = ctypes.CDLL(_SO)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                _missing.append(name)  # tests/test_abi.py asserts this list is empty
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def missing_symbols():
+    load()
+    return list(_missing)
+
+
+def last_error():
+    return load().dc_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("declip_b200 %s failed (rc=%d): %s" % (what, rc, last_error()))
+
+
+def init(device_index):
+    """dc_init once per device (checks compute capability 10.x; raises otherwise)."""
+    lib = load()
+    if device_index not in _inited_devices:
+        check(lib.dc_init(int(device_index)), "dc_init")
+        _inited_devices.add(device_index)
+    return lib
+
+
+def launch_count():
+    return int(load().dc_launch_count())

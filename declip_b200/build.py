@@ -1,0 +1,70 @@
+"""Builds declip_b200/_C.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+No torch headers are involved: the library is plain CUDA C++ behind `include/declip_b200.h`
+and is loaded with ctypes (see `_lib.py`).  Object files are cached under `build/` keyed on the
+source mtime so an incremental rebuild only recompiles what changed.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "_C.so")
+OBJ_DIR = os.path.join(ROOT, "build", "obj")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps_mtime():
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(ROOT, "include", "declip_b200.h"))
+    return max(os.path.getmtime(h) for h in hdrs)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    spath = os.path.join(CSRC, src)
+    if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(spath), _deps_mtime()):
+        return obj, ""
+    cmd = [NVCC] + ARCH + CFLAGS + ["-I", os.path.join(ROOT, "include"), "-c", spath, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    return obj, r.stderr
+
+
+def build(verbose=False, force=False):
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = _sources()
+    if force:
+        for s in srcs:
+            o = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
+            if os.path.exists(o):
+                os.remove(o)
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    objs = [o for o, _ in results]
+    log = "\n".join(l for _, l in results if l)
+    if verbose and log:
+        print(log)
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

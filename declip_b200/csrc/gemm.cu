@@ -1,0 +1,389 @@
+// declip_b200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] (op)= epilogue(alpha * sum_k A(m,k) * B(n,k)),  bf16 operands, fp32 accumulate in TMEM.
+//
+// One CTA per SM (persistent, static tile schedule, n-fastest so concurrently running CTAs share
+// the same A rows / the whole of B through L2).  256 threads:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor 2-D boxes -> 128B-swizzled smem stages)
+//   warp 1   : UMMA issuer   (one elected lane, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
+//   warps 4-7: epilogue      (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global)
+// Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue; the epilogue of
+// tile i overlaps the main loop of tile i+1), and the tile loop itself.
+//
+// Operand "major-ness" is a template parameter so forward (K-major x K-major), dgrad
+// (K-major x MN-major) and wgrad (MN-major x MN-major) all read the tensors where they lie in
+// HBM — no transposed copies are ever written.
+//
+// Replaces (reference, /root/reference): every nn.Linear/F.linear/`@` on the training hot path —
+// prototype/model/image_encoder/base_transformer.py:33-41, visual_transformer.py:56,72,
+// text_encoder/text_transformer.py:203, model/clip.py:140-141 — and their autograd backward.
+#include "common.cuh"
+#include "internal.h"
+
+namespace dc {
+
+struct GemmKParams {
+  int M, N, K;
+  int num_m, num_n, splits, kb_per_split, total_kb, num_tiles;
+  int epi;
+  float alpha;
+  void* out;
+  int ldo;
+  void* out2;
+  int ldo2;
+  const float* bias;
+  const bf16* aux;
+  int ldaux;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// 8 consecutive output columns of one row.
+__device__ __forceinline__ void epilogue8(const GemmKParams& p, int row, int col, const uint32_t* acc /*8 fp32 bits*/) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+  if (p.bias != nullptr && p.epi != DC_EPI_F32_ATOMIC && p.epi != DC_EPI_BF16_DGELU) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  const size_t o = static_cast<size_t>(row) * p.ldo + col;
+  switch (p.epi) {
+    case DC_EPI_BF16: {
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+    } break;
+    case DC_EPI_BF16_GELU: {
+      uint4 u, h;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out2) + static_cast<size_t>(row) * p.ldo2 + col) = u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+      h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+      h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = h;
+    } break;
+    case DC_EPI_BF16_RESID: {
+      const uint4 r = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
+      float2 f;
+      f = unpack_bf16x2(r.x); v[0] += f.x; v[1] += f.y;
+      f = unpack_bf16x2(r.y); v[2] += f.x; v[3] += f.y;
+      f = unpack_bf16x2(r.z); v[4] += f.x; v[5] += f.y;
+      f = unpack_bf16x2(r.w); v[6] += f.x; v[7] += f.y;
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+    } break;
+    case DC_EPI_BF16_DGELU: {
+      const uint4 r = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
+      float2 f;
+      f = unpack_bf16x2(r.x); v[0] *= quick_gelu_grad(f.x); v[1] *= quick_gelu_grad(f.y);
+      f = unpack_bf16x2(r.y); v[2] *= quick_gelu_grad(f.x); v[3] *= quick_gelu_grad(f.y);
+      f = unpack_bf16x2(r.z); v[4] *= quick_gelu_grad(f.x); v[5] *= quick_gelu_grad(f.y);
+      f = unpack_bf16x2(r.w); v[6] *= quick_gelu_grad(f.x); v[7] *= quick_gelu_grad(f.y);
+      uint4 w;
+      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+    } break;
+    case DC_EPI_F32: {
+      float* dst = static_cast<float*>(p.out) + o;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } break;
+    case DC_EPI_F32_ATOMIC: {
+      float* dst = static_cast<float*>(p.out) + o;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                   "f"(v[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                   "f"(v[7])
+                   : "memory");
+    } break;
+    default: break;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m * p.num_n;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int mn = t - split * tiles_mn;
+        const int m_blk = mn / p.num_n;
+        const int n_blk = mn - m_blk * p.num_n;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a)
+              tma_load_2d(sa + a * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + a * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_2d(sb + a * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + a * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.total_kb, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows (16 * 128 B).
+            const uint64_t adesc = A_MN ? umma_smem_desc(sa + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (TMEM -> regs -> global)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn;
+      const int mn = t - split * tiles_mn;
+      const int m_blk = mn / p.num_n;
+      const int n_blk = mn - m_blk * p.num_n;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < p.N) epilogue8(p, row, col, &r[g * 8]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
+  count_launch();
+  return 0;
+}
+
+int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error("gemm: empty problem");
+  if ((a.N & 7) || (a.lda & 7) || (a.ldb & 7) || (a.ldo & 3)) return set_error("gemm: N, lda, ldb must be multiples of 8");
+  if (a.epilogue < 0 || a.epilogue > DC_EPI_F32_ATOMIC) return set_error("gemm: bad epilogue");
+  if ((a.epilogue == DC_EPI_BF16_RESID || a.epilogue == DC_EPI_BF16_DGELU) && a.aux == nullptr)
+    return set_error("gemm: epilogue needs aux");
+  if (a.epilogue == DC_EPI_BF16_GELU && a.out2 == nullptr) return set_error("gemm: GELU epilogue needs out2");
+
+  int BN = a.block_n;
+  const int sms = sm_count();
+  if (BN == 0) {
+    // Pick the tile width that minimises (waves x per-tile cost); 256 is ~15 % more efficient per flop.
+    const long long nm = (a.M + BM - 1) / BM;
+    auto cost = [&](int bn) {
+      long long tiles = nm * ((a.N + bn - 1) / bn);
+      long long waves = (tiles + sms - 1) / sms;
+      return static_cast<double>(waves) * bn * (bn == 256 ? 1.0 : 1.15);
+    };
+    BN = (a.N <= 128 || cost(128) < cost(256)) ? 128 : 256;
+  }
+  if (BN != 128 && BN != 256) return set_error("gemm: block_n must be 128 or 256");
+
+  GemmKParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.num_m = (a.M + BM - 1) / BM;
+  p.num_n = (a.N + BN - 1) / BN;
+  p.total_kb = (a.K + BK - 1) / BK;
+  int splits = a.splits;
+  if (a.epilogue != DC_EPI_F32_ATOMIC) splits = 1;
+  if (splits <= 0) {
+    const int tiles = p.num_m * p.num_n;
+    splits = 1;
+    if (tiles < sms) {
+      splits = (2 * sms + tiles - 1) / tiles;
+      const int max_splits = (p.total_kb + 3) / 4;  // at least 4 k-blocks per split
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > p.total_kb) splits = p.total_kb;
+  p.kb_per_split = (p.total_kb + splits - 1) / splits;
+  p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.num_tiles = p.num_m * p.num_n * p.splits;
+  p.epi = a.epilogue;
+  p.alpha = a.alpha;
+  p.out = a.out; p.ldo = a.ldo;
+  p.out2 = a.out2; p.ldo2 = a.ldo2;
+  p.bias = a.bias;
+  p.aux = static_cast<const bf16*>(a.aux); p.ldaux = a.ldaux;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major operand [rows, K]: box {64 k, rows_per_tile}.  MN-major operand [K, mn]: box {64 mn, 64 k}.
+  if (!a.a_mn_major) rc = make_tmap_2d(&tmA, a.A, a.K, a.M, a.lda, 64, BM);
+  else               rc = make_tmap_2d(&tmA, a.A, a.M, a.K, a.lda, 64, BK);
+  if (rc) return rc;
+  if (!a.b_mn_major) rc = make_tmap_2d(&tmB, a.B, a.K, a.N, a.ldb, 64, BN);
+  else               rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 64, BK);
+  if (rc) return rc;
+
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+#define DC_LAUNCH(BN_, AM_, BM_) return launch_gemm<BN_, AM_, BM_>(tmA, tmB, p, grid, stream)
+  if (BN == 256) {
+    if (!a.a_mn_major && !a.b_mn_major) DC_LAUNCH(256, false, false);
+    if (!a.a_mn_major && a.b_mn_major) DC_LAUNCH(256, false, true);
+    if (a.a_mn_major && !a.b_mn_major) DC_LAUNCH(256, true, false);
+    DC_LAUNCH(256, true, true);
+  } else {
+    if (!a.a_mn_major && !a.b_mn_major) DC_LAUNCH(128, false, false);
+    if (!a.a_mn_major && a.b_mn_major) DC_LAUNCH(128, false, true);
+    if (a.a_mn_major && !a.b_mn_major) DC_LAUNCH(128, true, false);
+    DC_LAUNCH(128, true, true);
+  }
+#undef DC_LAUNCH
+}
+
+}  // namespace dc
+
+extern "C" int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream) {
+  if (args == nullptr) return dc::set_error("dc_gemm_bf16: null args");
+  return dc::gemm_bf16(*args, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,31 @@
+// declip_b200 — host-side internals shared by the translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/declip_b200.h"
+
+namespace dc {
+
+int set_error(const char* msg);
+int set_error_cuda(const char* what, cudaError_t e);
+void count_launch();
+int sm_count();
+
+// 2-D bf16 tensor map, 128-byte swizzle.  `inner` = contiguous extent (elements), `outer` = rows,
+// `ld` = row stride (elements); box = {box_inner (must be 64 -> 128 B), box_outer <= 256}.
+// OOB elements are zero-filled by the TMA unit, so ragged M/N/K tails need no special casing.
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
+                 int box_outer);
+
+// launchers implemented in the .cu files, used by the composite encoders
+int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream);
+
+}  // namespace dc
+
+#define DC_CHECK_LAUNCH(what)                                         \
+  do {                                                                \
+    cudaError_t e__ = cudaGetLastError();                             \
+    if (e__ != cudaSuccess) return dc::set_error_cuda(what, e__);     \
+    dc::count_launch();                                               \
+  } while (0)

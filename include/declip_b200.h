@@ -1,0 +1,163 @@
+/* declip_b200 — C ABI of the B200-native CLIP/DeCLIP dual-encoder training path.
+ *
+ * The reference (Sense-GVT/DeCLIP) is pure Python/PyTorch and has NO FFI of its own; its
+ * de-facto operator interface is the nn.Module forward signatures reached through
+ * model_entry() (prototype/model/__init__.py:15-21).  This header is therefore the boundary a
+ * maintainer would bind with ctypes from those modules; every entry point
+ * cites the reference op site (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless noted.
+ *   - every call enqueues work on `stream` (a cudaStream_t) and returns immediately.
+ *   - return 0 on success, non-zero on failure; dc_last_error() gives the text.  Never throws.
+ *   - the library never allocates or frees device memory and keeps no pointer after a call
+ *     returns (TMA descriptors are rebuilt/cached by value, keyed on the pointer + shape).
+ *   - bf16 = storage dtype of activations and weight shadows; fp32 = master weights, biases,
+ *     LayerNorm affine, statistics, gradients of parameters, loss.
+ *   - activations are token-major [tokens, width] ("NLD": row = sample*L + position).
+ */
+#ifndef DECLIP_B200_H_
+#define DECLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dc_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ library */
+int dc_version(void);
+const char* dc_last_error(void);
+/* Binds the driver entry points, checks the device is compute capability 10.x, raises the
+ * dynamic shared-memory limits of every kernel.  Must be called once per process/device. */
+int dc_init(int device);
+int dc_sm_count(void);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
+ * out[M,N] (op)= epilogue(alpha * sum_k A(m,k) * B(n,k))
+ *   a_mn_major = 0: A stored [M,K] row-major (K contiguous);  1: A stored [K,M] row-major.
+ *   b_mn_major = 0: B stored [N,K] row-major (K contiguous);  1: B stored [K,N] row-major.
+ * Replaces every nn.Linear / F.linear / `@` on the hot path:
+ *   base_transformer.py:33 (MultiheadAttention in/out proj), :35-41 (c_fc, c_proj),
+ *   visual_transformer.py:56 (conv1 as patch GEMM), :72 (x @ proj), text_transformer.py:203,
+ *   clip.py:140-141 (logit strips), and their autograd backward (dgrad / wgrad).
+ * lda/ldb/ldo/ldo2/ldaux are row strides in ELEMENTS and must be multiples of 8; N % 8 == 0. */
+enum {
+  DC_EPI_BF16 = 0,       /* out(bf16)  = alpha*acc + bias                                   */
+  DC_EPI_BF16_GELU = 1,  /* out2(bf16) = u = alpha*acc + bias ; out(bf16) = u*sigmoid(1.702u) */
+  DC_EPI_BF16_RESID = 2, /* out(bf16)  = alpha*acc + bias + aux(bf16)                        */
+  DC_EPI_BF16_DGELU = 3, /* out(bf16)  = alpha*acc * quickgelu'(aux(bf16))                   */
+  DC_EPI_F32 = 4,        /* out(fp32)  = alpha*acc + bias                                   */
+  DC_EPI_F32_ATOMIC = 5  /* out(fp32) += alpha*acc   (split-K allowed; red.global.add.v4.f32) */
+};
+typedef struct {
+  const void* A; int lda; int a_mn_major;
+  const void* B; int ldb; int b_mn_major;
+  int M, N, K;
+  int epilogue;
+  float alpha;
+  void* out; int ldo;
+  void* out2; int ldo2;
+  const float* bias;          /* [N] fp32 or NULL */
+  const void* aux; int ldaux; /* bf16 [M,N] or NULL */
+  int splits;                 /* split-K factor, 0 = auto (only DC_EPI_F32_ATOMIC may split) */
+  int block_n;                /* 0 = auto, else 128 or 256 */
+} dc_gemm_args;
+int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
+
+/* ------------------------------------------------------------------ row kernels (HBM-bound)
+ * LayerNorm over the last dim (eps 1e-5): base_transformer.py:10-18, visual_transformer.py:63,69,
+ * text_transformer.py:194.  x,y bf16 [rows,width]; gamma,beta fp32; mean,rstd fp32 [rows] saved
+ * for backward.  width % 256 == 0, width <= 1024. */
+int dc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int rows, int width, float eps, dc_stream_t stream);
+/* dx(bf16) = [dres +] LN'(dy); dgamma,dbeta (fp32 [width]) are ACCUMULATED (+=). dres may be NULL. */
+int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int width,
+                     dc_stream_t stream);
+/* out[c] += sum_r x[r,c] (bf16 in, fp32 accumulate): bias gradients of every Linear. */
+int dc_colsum_bf16(const void* x, int ldx, float* out, int rows, int cols, dc_stream_t stream);
+/* fp32 -> bf16 cast of n elements (weight shadows). */
+int dc_cast_f32_bf16(const float* src, void* dst, size_t n, dc_stream_t stream);
+/* table-driven multi-tensor cast: table (device) holds n_tensors entries {src, dst, numel}. */
+typedef struct { const float* src; void* dst; unsigned long long numel; } dc_cast_entry;
+int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsigned long long max_numel,
+                           dc_stream_t stream);
+
+/* ------------------------------------------------------------------ attention (L <= 80, head_dim 64)
+ * softmax(q k^T / sqrt(64) [+ causal mask]) v per (sample, head): base_transformer.py:44-48 via
+ * nn.MultiheadAttention; causal mask text_transformer.py:136-142.
+ * qkv bf16 [batch*L, 3*width] (q | k | v, heads contiguous inside each), out bf16 [batch*L, width],
+ * lse fp32 [batch*heads*L] saved for backward. */
+int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal,
+                     dc_stream_t stream);
+int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
+                     int L, int heads, int causal, dc_stream_t stream);
+
+/* ------------------------------------------------------------------ embeddings
+ * ViT: conv1 with kernel == stride == patch is a GEMM over non-overlapping patches
+ * (visual_transformer.py:56-59).  images fp32 NCHW [B,3,R,R] (channel offset/stride allow the
+ * DeCLIP 6-channel two-view layout, declip.py:199) -> patches bf16 [B*G*G, 3*P*P] (c,py,px order). */
+int dc_patchify(const float* images, long long sample_stride, void* patches, int batch, int res, int patch,
+                dc_stream_t stream);
+/* tokens[b,0,:] = cls + pos[0]; tokens[b,1+p,:] = patch_out[b*G2+p,:] + pos[1+p]
+ * (visual_transformer.py:60-62).  patch_out bf16 [B*G2,width]; cls fp32 [width]; pos fp32 [G2+1,width]. */
+int dc_vit_assemble(const void* patch_out, const float* cls, const float* pos, void* tokens, int batch, int g2,
+                    int width, dc_stream_t stream);
+/* text_transformer.py:188-190: x[b,l,:] = table[ids[b,l],:] + pos[l,:]; table,pos fp32; ids int64. */
+int dc_text_embed(const long long* ids, const float* table, const float* pos, void* x, int batch, int L,
+                  int width, dc_stream_t stream);
+/* dtable[ids[b,l],:] += dx[b,l,:]  (fp32 atomics) ; dpos[l,:] += sum_b dx[b,l,:] */
+int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, int batch, int L,
+                      int width, dc_stream_t stream);
+/* rows gather / scatter (cls token rows, EOT rows: visual_transformer.py:69, text_transformer.py:203):
+ * dst[i,:] = src[idx[i],:]  /  dst[idx[i],:] = src[i,:]  (bf16 rows, int32 row indices). */
+int dc_gather_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream);
+int dc_scatter_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream);
+/* eot[b] = b*L + argmax_l ids[b,l]  (text_transformer.py:203) */
+int dc_eot_index(const long long* ids, int* eot, int batch, int L, dc_stream_t stream);
+
+/* ------------------------------------------------------------------ contrastive head
+ * clip.py:129-130: y = x / (||x|| + eps) row-wise; x fp32 [n,dim] -> y bf16, inv fp32 [n] = 1/(||x||+eps). */
+int dc_l2norm_fwd(const float* x, void* y, float* inv, int n, int dim, float eps, dc_stream_t stream);
+/* dx(fp32) = inv * (dy - yhat * <dy, yhat> * c) with c = ||x||*inv (==1 for eps=0); dy fp32, yhat bf16. */
+int dc_l2norm_bwd(const float* dy, const void* y, const float* inv, float* dx, int n, int dim, float eps,
+                  dc_stream_t stream);
+/* loss.py:40-50 (ClipInfoCELoss) on one logit strip, fused with its backward and with
+ * misc.py:415-428 (accuracy top-1/top-5):  logits fp32 [rows,cols], label[r] = label0 + r.
+ *   loss_sum  += sum_r (lse_r - logit[r,label_r])           (fp32 atomic)
+ *   top1/top5 += #{r : rank of the label among the row < 1 / < 5}
+ *   dlogits (bf16 [rows,cols], may be NULL) = gscale * (softmax(row) - onehot(label))      */
+int dc_ce_strip(const float* logits, int ld, int rows, int cols, int label0, float gscale, float* loss_sum,
+                int* top1, int* top5, void* dlogits, int lddl, float* lse_out, dc_stream_t stream);
+
+/* ------------------------------------------------------------------ composite encoders (C++ executors)
+ * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.
+ * Weight/grad tables are arrays of device pointers in the order documented in encoder.h order
+ * (see declip_b200/csrc/encoder.cu: DC_LAYER_* / DC_VIT_* / DC_TEXT_* indices). */
+typedef struct {
+  int layers, width, heads, seq_len, causal;
+  int batch;
+  int embed_dim;
+  int res, patch; /* ViT only */
+  int vocab;      /* text only */
+} dc_tower_cfg;
+size_t dc_tower_workspace_bytes(const dc_tower_cfg* cfg);
+int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sample_stride,
+                   const void* const* w_bf16, const float* const* w_f32, void* workspace, float* features,
+                   dc_stream_t stream);
+int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* const* w_bf16,
+                    const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream);
+int dc_text_forward(const dc_tower_cfg* cfg, const long long* ids, const void* const* w_bf16,
+                    const float* const* w_f32, void* workspace, float* features, dc_stream_t stream);
+int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float* dfeatures,
+                     const void* const* w_bf16, const float* const* w_f32, float* const* grads, void* workspace,
+                     dc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECLIP_B200_H_ */
