@@ -1,0 +1,35 @@
+"""TEST INFRASTRUCTURE — golden-vector format shared by tools/make_golden.py and the tests."""
+import os
+
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+SAMPLE = 1024
+
+CASES = {
+    # name: dict(batch, v_layers, t_layers, embed_dim, seed)
+    "clip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=1),
+    "clip_vitb32_l12_b32": dict(batch=32, v_layers=12, t_layers=12, embed_dim=512, seed=0),   # BASELINE configs[0]
+}
+
+
+def sample_index(numel):
+    step = max(1, numel // SAMPLE)
+    return torch.arange(0, numel, step)[:SAMPLE]
+
+
+def summarise_grads(grads):
+    """Per-parameter: L2 norm + a deterministic strided sample (full tensor when small)."""
+    out = {}
+    for k, g in grads.items():
+        g = g.detach().float().reshape(-1)
+        out[k] = {"norm": g.norm().item(), "sample": g[sample_index(g.numel())].clone(), "numel": g.numel()}
+    return out
+
+
+def path(name):
+    return os.path.join(GOLDEN_DIR, name + ".pt")
+
+
+def load(name):
+    return torch.load(path(name), map_location="cpu", weights_only=False)

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE — imports the UNMODIFIED reference modules from /root/reference (build container
+only; the path does not exist on the GPU box) so golden vectors can be generated and the restatement in
+`oracle/clip_ref.py` can be pinned.  Recipe: SURVEY.md §8c / Appendix D.
+
+Nothing here is copied from the reference: the modules are imported where they lie.
+"""
+import gzip
+import os
+import sys
+import tempfile
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("DECLIP_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "prototype"))
+
+
+_ready = False
+_bpe_path = None
+
+
+def _fake_bpe():
+    """The real BPE merges file is a Google-Drive download, not in the repo (docs/dataset_prepare.md:33-37).
+    1 header + 48894 dummy merges gives len(tokenizer.encoder) == 49409 (simple_tokenizer.py:66-75)."""
+    global _bpe_path
+    if _bpe_path is None:
+        path = os.path.join(tempfile.gettempdir(), "declip_b200_fake_bpe.txt.gz")
+        if not os.path.exists(path):
+            with gzip.open(path, "wt") as f:
+                f.write("#version: fake\n")
+                for i in range(49152 - 256 - 2):
+                    f.write("a%d b%d\n" % (i, i))
+        _bpe_path = path
+    return _bpe_path
+
+
+def setup():
+    global _ready
+    if _ready:
+        return
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    for name in ("ipdb", "timm", "ftfy", "textaugment"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["ftfy"].fix_text = lambda s: s
+
+    class _EDA:   # identity text augmentation keeps DeCLIP parity deterministic (declip.py:203-212)
+        def synonym_replacement(self, s): return s
+        def random_swap(self, s): return s
+        def random_deletion(self, s): return s
+    sys.modules["textaugment"].EDA = _EDA
+    if not torch.cuda.is_available():
+        # hard-coded .cuda() calls: text_transformer.py:188, loss.py:43,45
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    _ready = True
+
+
+def build_clip_vitb32(embed_dim=512, image_kwargs=None, text_kwargs=None, use_allgather=False):
+    """prototype.model.model_entry({'type': 'clip_vitb32', ...}) — model/__init__.py:15-21, clip.py:158-165."""
+    setup()
+    from prototype.model import model_entry
+    ie = dict(embed_dim=embed_dim)
+    ie.update(image_kwargs or {})
+    te = dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False),
+              embed_dim=embed_dim)
+    te.update(text_kwargs or {})
+    cfg = dict(type="clip_vitb32", kwargs=dict(image_encode=ie, text_encode=te, clip=dict(use_allgather=use_allgather)))
+    return model_entry(cfg)
+
+
+def set_token_ids(model, ids, labels=None):
+    """Bypass the host BPE tokeniser with fixed ids (text_transformer.py:144-180)."""
+    def _tok(texts, context_length=77, return_length=False, mask_type=None):
+        if mask_type is not None:
+            return ids, labels
+        return ids
+    model.encode_text.tokenize = _tok
+
+
+def clip_loss_fn():
+    setup()
+    from prototype.loss_functions import ClipInfoCELoss
+    return ClipInfoCELoss()
+
+
+def reference_clip_step(sd, images, ids, embed_dim=512, v_layers=12, t_layers=12, backward=True):
+    """Reference forward + ClipInfoCELoss + backward on the given state_dict / inputs (CPU fp32)."""
+    model = build_clip_vitb32(embed_dim, dict(layers=v_layers), dict(transformer_layers=t_layers)).train()
+    missing, unexpected = model.load_state_dict(sd, strict=True), None
+    set_token_ids(model, ids)
+    B = images.shape[0]
+    li, lt = model({"images": images, "captions": [["x"]] * B})
+    loss, labels = clip_loss_fn()(li, lt)
+    out = {"loss": loss.detach(), "logits_per_image": li.detach(), "logits_per_text": lt.detach(), "labels": labels}
+    with torch.no_grad():
+        out["image_features"] = model.encode_image(images)
+        out["text_features"] = model.encode_text(["x"] * B)
+    if backward:
+        loss.backward()
+        out["grads"] = {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}
+    return out, model

@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE (oracle side) — deterministic synthetic weights and inputs.
+
+Both the reference modules (imported from /root/reference in the build container by
+`oracle/ref_harness.py`) and the CUDA path load the SAME state_dict produced here, so parity never
+depends on reproducing the reference's RNG call order.  Keys/shapes follow the reference's
+state_dict (prototype/model/clip.py:51-60, image_encoder/visual_transformer.py:6-27,
+text_encoder/text_transformer.py:27-44, image_encoder/base_transformer.py:29-42).
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / --impl reference legs may
+import this package.
+"""
+import math
+import zlib
+
+import torch
+
+VOCAB = 49409          # simple_tokenizer.py:66-75 : 49408 BPE/byte entries + <|mask|>
+SOT, EOT, MASK = 49407, 49408, 49406
+
+
+def _gen(key, seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+    return g
+
+
+def _randn(key, seed, shape, std):
+    return torch.randn(*shape, generator=_gen(key, seed), dtype=torch.float32) * std
+
+
+def _block_keys(prefix, width):
+    return [
+        (prefix + "attn.in_proj_weight", (3 * width, width), width ** -0.5),
+        (prefix + "attn.in_proj_bias", (3 * width,), 0.02),
+        (prefix + "attn.out_proj.weight", (width, width), width ** -0.5),
+        (prefix + "attn.out_proj.bias", (width,), 0.02),
+        (prefix + "ln_1.weight", (width,), None),
+        (prefix + "ln_1.bias", (width,), 0.02),
+        (prefix + "mlp.c_fc.weight", (4 * width, width), (2 * width) ** -0.5),
+        (prefix + "mlp.c_fc.bias", (4 * width,), 0.02),
+        (prefix + "mlp.c_proj.weight", (width, 4 * width), (2 * width) ** -0.5 * 0.5),
+        (prefix + "mlp.c_proj.bias", (width,), 0.02),
+        (prefix + "ln_2.weight", (width,), None),
+        (prefix + "ln_2.bias", (width,), 0.02),
+    ]
+
+
+def clip_vit_state_dict(seed=0, embed_dim=512, v_layers=12, t_layers=12, v_width=768, t_width=512, res=224, patch=32,
+                        ctx=77, vocab=VOCAB):
+    """state_dict for `clip_vitb32` (clip.py:158-165) with overridable depth for small test models."""
+    spec = [("logit_scale", (1,), "logit")]
+    g2 = (res // patch) ** 2
+    spec += [
+        ("visual.class_embedding", (v_width,), v_width ** -0.5),
+        ("visual.positional_embedding", (g2 + 1, v_width), 0.01 * 4),
+        ("visual.proj", (v_width, embed_dim), v_width ** -0.5),
+        ("visual.conv1.weight", (v_width, 3, patch, patch), (3 * patch * patch) ** -0.5),
+        ("visual.ln_pre.weight", (v_width,), None), ("visual.ln_pre.bias", (v_width,), 0.02),
+        ("visual.ln_post.weight", (v_width,), None), ("visual.ln_post.bias", (v_width,), 0.02),
+    ]
+    for i in range(v_layers):
+        spec += _block_keys("visual.transformer.resblocks.%d." % i, v_width)
+    spec += [
+        ("encode_text.positional_embedding", (ctx, t_width), 0.01 * 4),
+        ("encode_text.token_embedding.weight", (vocab, t_width), 0.02 * 4),
+        ("encode_text.ln_final.weight", (t_width,), None), ("encode_text.ln_final.bias", (t_width,), 0.02),
+        ("encode_text.text_projection.weight", (embed_dim, t_width), t_width ** -0.5),
+        ("encode_text.text_projection.bias", (embed_dim,), 0.02),
+    ]
+    for i in range(t_layers):
+        spec += _block_keys("encode_text.transformer.resblocks.%d." % i, t_width)
+    sd = {}
+    for key, shape, std in spec:
+        if std == "logit":
+            sd[key] = torch.full(shape, math.log(1 / 0.07), dtype=torch.float32)   # clip.py:59
+        elif std is None:   # LayerNorm gain: 1 + noise so the affine path is exercised
+            sd[key] = 1.0 + _randn(key, seed, shape, 0.1)
+        else:
+            sd[key] = _randn(key, seed, shape, std)
+    return sd
+
+
+def synth_images(batch, seed=0, channels=3, res=224):
+    return torch.randn(batch, channels, res, res, generator=_gen("images", seed), dtype=torch.float32)
+
+
+def synth_token_ids(batch, seed=0, ctx=77, vocab=VOCAB):
+    """int64 [B,ctx]: SOT, random body of length U[8,ctx-2], EOT (= max id so argmax finds it;
+    text_transformer.py:203), zero padding — the layout `tokenize` produces (text_transformer.py:144-180)."""
+    g = _gen("ids", seed)
+    ids = torch.zeros(batch, ctx, dtype=torch.int64)
+    lens = torch.randint(8, ctx - 1, (batch,), generator=g)
+    body = torch.randint(1, 49000, (batch, ctx), generator=g)
+    for b in range(batch):
+        n = int(lens[b])
+        ids[b, 0] = SOT
+        ids[b, 1:1 + n] = body[b, :n]
+        ids[b, 1 + n] = EOT
+    return ids

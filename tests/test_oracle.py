@@ -1,0 +1,62 @@
+"""CPU: the oracle restatement (oracle/clip_ref.py) against the golden vectors produced by the
+reference's own modules (tools/make_golden.py).  fp32 vs fp32, so the tolerance is tight."""
+import pytest
+import torch
+
+from oracle import clip_ref, golden, synth
+
+
+def _run(name):
+    g = golden.load(name)
+    c = g["case"]
+    sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"],
+                                   t_layers=c["t_layers"])
+    images = synth.synth_images(c["batch"], seed=c["seed"])
+    ids = synth.synth_token_ids(c["batch"], seed=c["seed"])
+    return g, clip_ref.clip_step(sd, images, ids)
+
+
+@pytest.mark.parametrize("name", ["clip_vitb32_l2_b8", "clip_vitb32_l12_b32"])
+def test_restatement_matches_reference_golden(name):
+    g, out = _run(name)
+    assert abs(out["loss"].item() - g["loss"]) <= 2e-5
+    torch.testing.assert_close(out["image_features"], g["image_features"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out["text_features"], g["text_features"], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out["logits_per_image"], g["logits_per_image"], rtol=2e-4, atol=5e-4)
+    torch.testing.assert_close(out["logits_per_text"], g["logits_per_text"], rtol=2e-4, atol=5e-4)
+    assert torch.equal(out["labels"], g["labels"])
+    # every trainable parameter of the reference has a gradient here, and they agree
+    assert set(out["grads"]) == set(g["grads"])
+    assert "visual.conv1.weight" not in g["grads"]          # frozen: visual_transformer.py:12,45-51
+    for k, ref in g["grads"].items():
+        mine = out["grads"][k].reshape(-1)
+        samp = mine[golden.sample_index(mine.numel())]
+        denom = ref["sample"].norm().item() + 1e-12
+        assert (samp - ref["sample"]).norm().item() / denom <= 2e-3, k
+        assert abs(mine.norm().item() - ref["norm"]) <= 2e-3 * ref["norm"] + 1e-9, k
+
+
+def test_known_answers():
+    # initial CLIP loss ~ ln(N) at random init
+    g = golden.load("clip_vitb32_l12_b32")
+    import math
+    assert abs(g["loss"] - math.log(32)) < 0.5
+    ids = synth.synth_token_ids(16, seed=3)
+    assert (ids[:, 0] == synth.SOT).all()
+    assert (ids.max(dim=1).values == synth.EOT).all()
+    eot = ids.argmax(dim=1)
+    for b in range(16):
+        assert (ids[b, eot[b] + 1:] == 0).all()
+
+
+def test_logit_scale_clamp_semantics():
+    # clip.py:133-134: value clamped at 100 but gradient flows as exp(logit_scale)
+    ls = torch.tensor([5.5], requires_grad=True)
+    i = torch.nn.functional.normalize(torch.randn(4, 8), dim=-1)
+    t = torch.nn.functional.normalize(torch.randn(4, 8), dim=-1)
+    li, _, _, _ = clip_ref.clip_logits(i, t, ls)
+    assert torch.allclose(li, 100.0 * (i / i.norm(dim=-1, keepdim=True)) @ (t / (t.norm(dim=-1, keepdim=True) + 1e-10)).t(),
+                          atol=1e-4)
+    li.sum().backward()
+    raw = ((i / i.norm(dim=-1, keepdim=True)) @ (t / (t.norm(dim=-1, keepdim=True) + 1e-10)).t()).sum()
+    assert abs(ls.grad.item() - (torch.exp(torch.tensor(5.5)) * raw).item()) < 1e-2

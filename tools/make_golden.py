@@ -1,0 +1,46 @@
+"""Generates tests/golden/*.pt by executing the UNMODIFIED reference modules (imported from
+/root/reference — build container only) on the synthetic weights/inputs of oracle/synth.py.
+
+    python tools/make_golden.py            # all cases
+Committed beside the vectors so the provenance of every golden number is reproducible.
+"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import golden, ref_harness, synth  # noqa: E402
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 8)
+    os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
+    names = sys.argv[1:] or list(golden.CASES)
+    for name in names:
+        c = golden.CASES[name]
+        t0 = time.time()
+        sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"],
+                                       t_layers=c["t_layers"])
+        images = synth.synth_images(c["batch"], seed=c["seed"])
+        ids = synth.synth_token_ids(c["batch"], seed=c["seed"])
+        out, model = ref_harness.reference_clip_step(sd, images, ids, c["embed_dim"], c["v_layers"], c["t_layers"])
+        blob = {
+            "case": c, "torch": torch.__version__,
+            "generator": "tools/make_golden.py via oracle/ref_harness.py (reference @ /root/reference, CPU fp32)",
+            "loss": out["loss"].item(),
+            "logits_per_image": out["logits_per_image"].clone(), "logits_per_text": out["logits_per_text"].clone(),
+            "image_features": out["image_features"].clone(), "text_features": out["text_features"].clone(),
+            "labels": out["labels"].clone(),
+            "grads": golden.summarise_grads(out["grads"]),
+            "param_names": [k for k, _ in model.named_parameters()],
+            "trainable": [k for k, p in model.named_parameters() if p.requires_grad],
+        }
+        torch.save(blob, golden.path(name))
+        print("%s: loss %.6f, %d grads, %.1fs -> %s (%.1f KB)" % (name, blob["loss"], len(blob["grads"]), time.time() - t0,
+              golden.path(name), os.path.getsize(golden.path(name)) / 1024))
+
+
+if __name__ == "__main__":
+    main()
