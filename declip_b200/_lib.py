@@ -34,6 +34,7 @@ class GemmArgs(ctypes.Structure):
         ("bias", c_void_p),
         ("aux", c_void_p), ("ldaux", c_int),
         ("splits", c_int), ("block_n", c_int),
+        ("alpha_dev", c_void_p),
     ]
 
 
@@ -74,9 +75,12 @@ SIGNATURES = {
     "dc_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_eot_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
-    "dc_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
-    "dc_ce_strip": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
-                            c_int, c_void_p, c_void_p]),
+    "dc_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "dc_ce_strip_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "dc_ce_strip_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
+                                c_int, c_void_p]),
+    "dc_dot_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),

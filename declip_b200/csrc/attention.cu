@@ -1,0 +1,412 @@
+// declip_b200 — fused multi-head attention core for tiny sequences (L = 50 ViT-B/32, L = 77 causal
+// text), head_dim 64: softmax(q k^T / 8 [+ causal]) v, forward and backward, one CTA per
+// (sample, head).  The L x L score matrix never leaves the SM (the reference materialises it:
+// nn.MultiheadAttention(..., need_weights=True), image_encoder/base_transformer.py:44-48; causal
+// mask text_encoder/text_transformer.py:136-142).
+//
+// Design note: this core is 1.6 % of the step FLOPs and is bound by streaming
+// qkv/out (HBM) and by latency, not by tensor throughput; 50/77-row tiles would waste 22-60 % of a
+// 128-row tcgen05 tile.  It therefore uses warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate)
+// with ldmatrix-fed fragments; the projections around it (QKV, out-proj: 98 % of the attention
+// FLOPs) run on the tcgen05 GEMM in gemm.cu.
+#include "common.cuh"
+#include "internal.h"
+
+namespace dc {
+
+constexpr int HD = 64;        // head dim
+constexpr int HS = HD + 8;    // smem row stride (elements) of [*, 64] tiles: 144 B -> conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragment (16 x 16) of a row-major [M][K] smem matrix (stride ld elements) at (m0, k0).
+__device__ __forceinline__ void load_a(const bf16* s, int ld, int m0, int k0, uint32_t (&a)[4]) {
+  const int lane = lane_id(), mat = lane >> 3, r = lane & 7;
+  ldsm_x4(smem_u32(s + (m0 + (mat & 1) * 8 + r) * ld + k0 + (mat >> 1) * 8), a[0], a[1], a[2], a[3]);
+}
+// A fragment of A(m,k) = S[k][m] (matrix stored [K][M]).
+__device__ __forceinline__ void load_a_t(const bf16* s, int ld, int m0, int k0, uint32_t (&a)[4]) {
+  const int lane = lane_id(), mat = lane >> 3, r = lane & 7;
+  ldsm_x4_t(smem_u32(s + (k0 + (mat >> 1) * 8 + r) * ld + m0 + (mat & 1) * 8), a[0], a[1], a[2], a[3]);
+}
+// B fragments for two adjacent n-tiles (n0..n0+15) x k16 of B(k,n) = S[n][k] (stored [N][K]).
+__device__ __forceinline__ void load_b_nk(const bf16* s, int ld, int n0, int k0, uint32_t (&b)[4]) {
+  const int lane = lane_id(), mat = lane >> 3, r = lane & 7;
+  ldsm_x4(smem_u32(s + (n0 + (mat >> 1) * 8 + r) * ld + k0 + (mat & 1) * 8), b[0], b[1], b[2], b[3]);
+}
+// B fragments for two adjacent n-tiles of B(k,n) = S[k][n] (stored [K][N]).
+__device__ __forceinline__ void load_b_kn(const bf16* s, int ld, int n0, int k0, uint32_t (&b)[4]) {
+  const int lane = lane_id(), mat = lane >> 3, r = lane & 7;
+  ldsm_x4_t(smem_u32(s + (k0 + (mat & 1) * 8 + r) * ld + n0 + (mat >> 1) * 8), b[0], b[1], b[2], b[3]);
+}
+
+// Cooperative load of one head's [L, 64] slice (row stride `ld` elements in global) into smem [LP][HS]; rows >= L zeroed.
+template <int LP>
+__device__ __forceinline__ void load_head(const bf16* __restrict__ g, size_t ld, int L, bf16* s) {
+  for (int i = threadIdx.x; i < LP * 8; i += blockDim.x) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < L) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
+    *reinterpret_cast<uint4*>(s + r * HS + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int LP>
+__global__ void __launch_bounds__(LP * 2) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                          float* __restrict__ lse, int L, int heads, int causal) {
+  constexpr int NT = LP / 8;   // key n-tiles
+  constexpr int KT = LP / 16;  // key k-steps for P V
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sK = sQ + LP * HS;
+  bf16* sV = sK + LP * HS;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int D = heads * HD;
+  const size_t ld = static_cast<size_t>(3) * D;
+  const bf16* base = qkv + static_cast<size_t>(b) * L * ld + h * HD;
+  load_head<LP>(base, ld, L, sQ);
+  load_head<LP>(base + D, ld, L, sK);
+  load_head<LP>(base + 2 * D, ld, L, sV);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  if (m0 >= L) return;  // whole warp is padding
+
+  float s[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < HD / 16; ++k) {
+    uint32_t a[4];
+    load_a(sQ, HS, m0, k * 16, a);
+#pragma unroll
+    for (int n = 0; n < NT; n += 2) {
+      uint32_t bb[4];
+      load_b_nk(sK, HS, n * 8, k * 16, bb);
+      mma_bf16(s[n], a, bb[0], bb[1]);
+      mma_bf16(s[n + 1], a, bb[2], bb[3]);
+    }
+  }
+  // masked softmax over keys; rows r0 = m0+g, r1 = m0+g+8
+  const float scale = 0.125f;
+  const int r0 = m0 + g, r1 = r0 + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = n * 8 + 2 * t + i;
+      const bool ok0 = c < L && (!causal || c <= r0);
+      const bool ok1 = c < L && (!causal || c <= r1);
+      s[n][i] = ok0 ? s[n][i] * scale : -INFINITY;
+      s[n][2 + i] = ok1 ? s[n][2 + i] * scale : -INFINITY;
+      mx0 = fmaxf(mx0, s[n][i]);
+      mx1 = fmaxf(mx1, s[n][2 + i]);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  if (mx0 == -INFINITY) mx0 = 0.f;  // padded rows (>= L under causal masking never happens, but stay NaN-free)
+  if (mx1 == -INFINITY) mx1 = 0.f;
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      s[n][i] = __expf(s[n][i] - mx0);
+      s[n][2 + i] = __expf(s[n][2 + i] - mx1);
+      sum0 += s[n][i];
+      sum1 += s[n][2 + i];
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / fmaxf(sum0, 1e-30f), inv1 = 1.0f / fmaxf(sum1, 1e-30f);
+  if (t == 0 && lse != nullptr) {
+    float* l = lse + (static_cast<size_t>(b) * heads + h) * L;
+    if (r0 < L) l[r0] = mx0 + __logf(sum0);
+    if (r1 < L) l[r1] = mx1 + __logf(sum1);
+  }
+  // O = P V
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    uint32_t a[4];
+    a[0] = pack_bf16x2(s[2 * k][0] * inv0, s[2 * k][1] * inv0);
+    a[1] = pack_bf16x2(s[2 * k][2] * inv1, s[2 * k][3] * inv1);
+    a[2] = pack_bf16x2(s[2 * k + 1][0] * inv0, s[2 * k + 1][1] * inv0);
+    a[3] = pack_bf16x2(s[2 * k + 1][2] * inv1, s[2 * k + 1][3] * inv1);
+#pragma unroll
+    for (int n = 0; n < HD / 8; n += 2) {
+      uint32_t bb[4];
+      load_b_kn(sV, HS, n * 8, k * 16, bb);
+      mma_bf16(o[n], a, bb[0], bb[1]);
+      mma_bf16(o[n + 1], a, bb[2], bb[3]);
+    }
+  }
+  bf16* ob = out + static_cast<size_t>(b) * L * D + h * HD;
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    const int c = n * 8 + 2 * t;
+    if (r0 < L) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r0) * D + c) = pack_bf16x2(o[n][0], o[n][1]);
+    if (r1 < L) *reinterpret_cast<uint32_t*>(ob + static_cast<size_t>(r1) * D + c) = pack_bf16x2(o[n][2], o[n][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// dV = P^T dO ; dP = dO V^T ; dS = P * (dP - rowsum(dO*O)) / 8 ; dQ = dS K ; dK = dS^T Q.  P is recomputed
+// from the saved log-sum-exp.
+template <int LP>
+__global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
+                                                          const bf16* __restrict__ dout, const float* __restrict__ lse,
+                                                          bf16* __restrict__ dqkv, int L, int heads, int causal) {
+  constexpr int NT = LP / 8;
+  constexpr int KT = LP / 16;
+  constexpr int PS = LP + 8;  // row stride of the [LP][LP] P / dS tiles
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sK = sQ + LP * HS;
+  bf16* sV = sK + LP * HS;
+  bf16* sdO = sV + LP * HS;
+  bf16* sP = sdO + LP * HS;
+  bf16* sdS = sP + LP * PS;
+  float* sDelta = reinterpret_cast<float*>(sdS + LP * PS);
+
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int D = heads * HD;
+  const size_t ld = static_cast<size_t>(3) * D;
+  const bf16* base = qkv + static_cast<size_t>(b) * L * ld + h * HD;
+  const bf16* ob = out + static_cast<size_t>(b) * L * D + h * HD;
+  const bf16* dob = dout + static_cast<size_t>(b) * L * D + h * HD;
+  load_head<LP>(base, ld, L, sQ);
+  load_head<LP>(base + D, ld, L, sK);
+  load_head<LP>(base + 2 * D, ld, L, sV);
+  load_head<LP>(dob, D, L, sdO);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+
+  // delta[row] = sum_d dO[row][d] * O[row][d]; two lanes per row
+  {
+    const int r = m0 + (lane >> 1), half = lane & 1;
+    float acc = 0.f;
+    if (r < L) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = half * 32 + j * 8;
+        const uint4 uo = *reinterpret_cast<const uint4*>(ob + static_cast<size_t>(r) * D + c);
+        const uint4 ud = *reinterpret_cast<const uint4*>(sdO + r * HS + c);
+        float2 a, d;
+        a = unpack_bf16x2(uo.x); d = unpack_bf16x2(ud.x); acc += a.x * d.x + a.y * d.y;
+        a = unpack_bf16x2(uo.y); d = unpack_bf16x2(ud.y); acc += a.x * d.x + a.y * d.y;
+        a = unpack_bf16x2(uo.z); d = unpack_bf16x2(ud.z); acc += a.x * d.x + a.y * d.y;
+        a = unpack_bf16x2(uo.w); d = unpack_bf16x2(ud.w); acc += a.x * d.x + a.y * d.y;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) sDelta[r] = acc;
+  }
+  __syncwarp();
+
+  const float scale = 0.125f;
+  const int r0 = m0 + g, r1 = r0 + 8;
+  {
+    // S = Q K^T and dP = dO V^T for this warp's 16 query rows
+    float s[NT][4], dp[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) {
+      uint32_t aq[4], ad[4];
+      load_a(sQ, HS, m0, k * 16, aq);
+      load_a(sdO, HS, m0, k * 16, ad);
+#pragma unroll
+      for (int n = 0; n < NT; n += 2) {
+        uint32_t bk[4], bv[4];
+        load_b_nk(sK, HS, n * 8, k * 16, bk);
+        load_b_nk(sV, HS, n * 8, k * 16, bv);
+        mma_bf16(s[n], aq, bk[0], bk[1]);
+        mma_bf16(s[n + 1], aq, bk[2], bk[3]);
+        mma_bf16(dp[n], ad, bv[0], bv[1]);
+        mma_bf16(dp[n + 1], ad, bv[2], bv[3]);
+      }
+    }
+    const float* l = lse + (static_cast<size_t>(b) * heads + h) * L;
+    const float lse0 = (r0 < L) ? l[r0] : 0.f, lse1 = (r1 < L) ? l[r1] : 0.f;
+    const float dl0 = sDelta[r0], dl1 = sDelta[r1];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      float p[4], ds[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = n * 8 + 2 * t + i;
+        const bool ok0 = r0 < L && c < L && (!causal || c <= r0);
+        const bool ok1 = r1 < L && c < L && (!causal || c <= r1);
+        p[i] = ok0 ? __expf(s[n][i] * scale - lse0) : 0.f;
+        p[2 + i] = ok1 ? __expf(s[n][2 + i] * scale - lse1) : 0.f;
+        ds[i] = p[i] * (dp[n][i] - dl0) * scale;
+        ds[2 + i] = p[2 + i] * (dp[n][2 + i] - dl1) * scale;
+      }
+      const int c = n * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(sP + r0 * PS + c) = pack_bf16x2(p[0], p[1]);
+      *reinterpret_cast<uint32_t*>(sP + r1 * PS + c) = pack_bf16x2(p[2], p[3]);
+      *reinterpret_cast<uint32_t*>(sdS + r0 * PS + c) = pack_bf16x2(ds[0], ds[1]);
+      *reinterpret_cast<uint32_t*>(sdS + r1 * PS + c) = pack_bf16x2(ds[2], ds[3]);
+    }
+  }
+  __syncthreads();
+  if (m0 >= L) return;
+
+  bf16* dbase = dqkv + static_cast<size_t>(b) * L * ld + h * HD;
+  float acc[HD / 8][4];
+  auto zero_acc = [&]() {
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+  };
+  auto store_acc = [&](bf16* dst) {
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      const int c = n * 8 + 2 * t;
+      if (r0 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r0) * ld + c) = pack_bf16x2(acc[n][0], acc[n][1]);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r1) * ld + c) = pack_bf16x2(acc[n][2], acc[n][3]);
+    }
+  };
+  // dQ[q][d] = sum_key dS[q][key] K[key][d]
+  zero_acc();
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    uint32_t a[4];
+    load_a(sdS, PS, m0, k * 16, a);
+#pragma unroll
+    for (int n = 0; n < HD / 8; n += 2) {
+      uint32_t bb[4];
+      load_b_kn(sK, HS, n * 8, k * 16, bb);
+      mma_bf16(acc[n], a, bb[0], bb[1]);
+      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+    }
+  }
+  store_acc(dbase);
+  // dK[key][d] = sum_q dS[q][key] Q[q][d]   (this warp's rows are keys now)
+  zero_acc();
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    uint32_t a[4];
+    load_a_t(sdS, PS, m0, k * 16, a);
+#pragma unroll
+    for (int n = 0; n < HD / 8; n += 2) {
+      uint32_t bb[4];
+      load_b_kn(sQ, HS, n * 8, k * 16, bb);
+      mma_bf16(acc[n], a, bb[0], bb[1]);
+      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+    }
+  }
+  store_acc(dbase + D);
+  // dV[key][d] = sum_q P[q][key] dO[q][d]
+  zero_acc();
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    uint32_t a[4];
+    load_a_t(sP, PS, m0, k * 16, a);
+#pragma unroll
+    for (int n = 0; n < HD / 8; n += 2) {
+      uint32_t bb[4];
+      load_b_kn(sdO, HS, n * 8, k * 16, bb);
+      mma_bf16(acc[n], a, bb[0], bb[1]);
+      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+    }
+  }
+  store_acc(dbase + 2 * D);
+}
+
+template <int LP>
+static size_t attn_fwd_smem() { return static_cast<size_t>(3) * LP * HS * 2; }
+template <int LP>
+static size_t attn_bwd_smem() { return static_cast<size_t>(4) * LP * HS * 2 + static_cast<size_t>(2) * LP * (LP + 8) * 2 + LP * 4; }
+
+template <int LP>
+static int launch_fwd(const bf16* qkv, bf16* out, float* lse, int batch, int L, int heads, int causal, cudaStream_t st) {
+  auto kern = attn_fwd_kernel<LP>;
+  const size_t smem = attn_fwd_smem<LP>();
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_fwd)", e);
+    set = true;
+  }
+  kern<<<batch * heads, LP * 2, smem, st>>>(qkv, out, lse, L, heads, causal);
+  DC_CHECK_LAUNCH("attention_fwd");
+  return 0;
+}
+template <int LP>
+static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int batch, int L,
+                      int heads, int causal, cudaStream_t st) {
+  auto kern = attn_bwd_kernel<LP>;
+  const size_t smem = attn_bwd_smem<LP>();
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_bwd)", e);
+    set = true;
+  }
+  kern<<<batch * heads, LP * 2, smem, st>>>(qkv, out, dout, lse, dqkv, L, heads, causal);
+  DC_CHECK_LAUNCH("attention_bwd");
+  return 0;
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal,
+                     dc_stream_t stream) {
+  if (batch <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");
+  if (L <= 64)
+    return launch_fwd<64>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, L, heads, causal, st);
+  return launch_fwd<80>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, L, heads, causal, st);
+}
+
+int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
+                     int L, int heads, int causal, dc_stream_t stream) {
+  if (batch <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");
+  if (L <= 64)
+    return launch_bwd<64>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,
+                          static_cast<bf16*>(dqkv), batch, L, heads, causal, st);
+  return launch_bwd<80>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,
+                        static_cast<bf16*>(dqkv), batch, L, heads, causal, st);
+}
+
+}  // extern "C"

@@ -35,6 +35,7 @@ struct GemmKParams {
   const float* bias;
   const bf16* aux;
   int ldaux;
+  const float* alpha_dev;
 };
 
 constexpr int BM = 128;
@@ -52,10 +53,11 @@ struct GemmCfg {
 };
 
 // 8 consecutive output columns of one row.
-__device__ __forceinline__ void epilogue8(const GemmKParams& p, int row, int col, const uint32_t* acc /*8 fp32 bits*/) {
+__device__ __forceinline__ void epilogue8(const GemmKParams& p, float alpha, int row, int col,
+                                          const uint32_t* acc /*8 fp32 bits*/) {
   float v[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]) * alpha;
   if (p.bias != nullptr && p.epi != DC_EPI_F32_ATOMIC && p.epi != DC_EPI_BF16_DGELU) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
@@ -244,6 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM -> regs -> global)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -267,7 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int col = col0 + g * 8;
-            if (col < p.N) epilogue8(p, row, col, &r[g * 8]);
+            if (col < p.N) epilogue8(p, alpha, row, col, &r[g * 8]);
           }
         }
       }
@@ -354,6 +357,7 @@ int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   p.out2 = a.out2; p.ldo2 = a.ldo2;
   p.bias = a.bias;
   p.aux = static_cast<const bf16*>(a.aux); p.ldaux = a.ldaux;
+  p.alpha_dev = a.alpha_dev;
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -1,0 +1,718 @@
+// declip_b200 — HBM-bound row kernels: LayerNorm fwd/bwd, bias-gradient column sums, casts,
+// patch/token embedding, row gather/scatter, L2-normalise, cross-entropy on logit strips.
+// All loads/stores are 16-byte vectors, one warp per row where a row reduction is needed
+// (no shared memory, shuffle reductions), grids sized in multiples of the SM count.
+#include "common.cuh"
+#include "internal.h"
+
+namespace dc {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward — reference: image_encoder/base_transformer.py:10-18 (nn.LayerNorm, eps 1e-5).
+// One warp per row; the row lives in registers (NV 16-byte vectors per lane), two-pass variance.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, bf16* __restrict__ y,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     int rows, float eps) {
+  constexpr int W = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float g[NV][8], b[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    g[j][0] = g0.x; g[j][1] = g0.y; g[j][2] = g0.z; g[j][3] = g0.w;
+    g[j][4] = g1.x; g[j][5] = g1.y; g[j][6] = g1.z; g[j][7] = g1.w;
+    b[j][0] = b0.x; b[j][1] = b0.y; b[j][2] = b0.z; b[j][3] = b0.w;
+    b[j][4] = b1.x; b[j][5] = b1.y; b[j][6] = b1.z; b[j][7] = b1.w;
+  }
+  for (int row = warp; row < rows; row += nwarps) {
+    const bf16* xr = x + static_cast<size_t>(row) * W;
+    float v[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + (lane + 32 * j) * 8);
+      float2 f;
+      f = unpack_bf16x2(u.x); v[j][0] = f.x; v[j][1] = f.y;
+      f = unpack_bf16x2(u.y); v[j][2] = f.x; v[j][3] = f.y;
+      f = unpack_bf16x2(u.z); v[j][4] = f.x; v[j][5] = f.y;
+      f = unpack_bf16x2(u.w); v[j][6] = f.x; v[j][7] = f.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[j][i];
+    }
+    const float mean = warp_sum(s) * (1.0f / W);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / W) + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    bf16* yr = y + static_cast<size_t>(row) * W;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (v[j][i] - mean) * rstd * g[j][i] + b[j][i];
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + (lane + 32 * j) * 8) = w;
+    }
+  }
+}
+
+// LayerNorm backward: dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (register accumulation per lane across the
+// warp's rows, then shared-memory + global fp32 atomics once per block).
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const bf16* __restrict__ dres,
+                                                     bf16* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int rows) {
+  constexpr int W = NV * 256;
+  __shared__ float s_acc[2 * W];
+  for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float g[NV][8], ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    g[j][0] = g0.x; g[j][1] = g0.y; g[j][2] = g0.z; g[j][3] = g0.w;
+    g[j][4] = g1.x; g[j][5] = g1.y; g[j][6] = g1.z; g[j][7] = g1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; }
+  }
+  for (int row = warp; row < rows; row += nwarps) {
+    const size_t base = static_cast<size_t>(row) * W;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], gy[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      const uint4 ux = *reinterpret_cast<const uint4*>(x + base + c);
+      const uint4 ud = *reinterpret_cast<const uint4*>(dy + base + c);
+      float xv[8], dv[8];
+      float2 f;
+      f = unpack_bf16x2(ux.x); xv[0] = f.x; xv[1] = f.y;
+      f = unpack_bf16x2(ux.y); xv[2] = f.x; xv[3] = f.y;
+      f = unpack_bf16x2(ux.z); xv[4] = f.x; xv[5] = f.y;
+      f = unpack_bf16x2(ux.w); xv[6] = f.x; xv[7] = f.y;
+      f = unpack_bf16x2(ud.x); dv[0] = f.x; dv[1] = f.y;
+      f = unpack_bf16x2(ud.y); dv[2] = f.x; dv[3] = f.y;
+      f = unpack_bf16x2(ud.z); dv[4] = f.x; dv[5] = f.y;
+      f = unpack_bf16x2(ud.w); dv[6] = f.x; dv[7] = f.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[j][i] = (xv[i] - mu) * rs;
+        gy[j][i] = dv[i] * g[j][i];
+        s1 += gy[j][i];
+        s2 += gy[j][i] * xh[j][i];
+        ag[j][i] += dv[i] * xh[j][i];
+        ab[j][i] += dv[i];
+      }
+    }
+    const float c1 = warp_sum(s1) * (1.0f / W);
+    const float c2 = warp_sum(s2) * (1.0f / W);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = (lane + 32 * j) * 8;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs * (gy[j][i] - c1 - xh[j][i] * c2);
+      if (dres != nullptr) {
+        const uint4 ur = *reinterpret_cast<const uint4*>(dres + base + c);
+        float2 f;
+        f = unpack_bf16x2(ur.x); o[0] += f.x; o[1] += f.y;
+        f = unpack_bf16x2(ur.y); o[2] += f.x; o[3] += f.y;
+        f = unpack_bf16x2(ur.z); o[4] += f.x; o[5] += f.y;
+        f = unpack_bf16x2(ur.w); o[6] += f.x; o[7] += f.y;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + base + c) = w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[c + i], ag[j][i]);
+      atomicAdd(&s_acc[W + c + i], ab[j][i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_acc[i]);
+    atomicAdd(&dbeta[i], s_acc[W + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums (bias gradients): out[c] += sum_r x[r,c].  Block = 8 column-vectors x 32 row lanes,
+// 64 columns x ROWS_PER_BLOCK rows per block; warp loads are 4 rows x 128 contiguous bytes.
+constexpr int COLSUM_ROWS = 1024;
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ldx, float* __restrict__ out,
+                                                     int rows, int cols) {
+  __shared__ float s_part[32][65];
+  const int cv = threadIdx.x & 7;
+  const int rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cv * 8;
+  const int r0 = blockIdx.y * COLSUM_ROWS;
+  const int r1 = min(rows, r0 + COLSUM_ROWS);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+    for (int r = r0 + rl; r < r1; r += 32) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * ldx + c0);
+      float2 f;
+      f = unpack_bf16x2(u.x); a[0] += f.x; a[1] += f.y;
+      f = unpack_bf16x2(u.y); a[2] += f.x; a[3] += f.y;
+      f = unpack_bf16x2(u.z); a[4] += f.x; a[5] += f.y;
+      f = unpack_bf16x2(u.w); a[6] += f.x; a[7] += f.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_part[rl][cv * 8 + i] = a[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) s += s_part[r][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < cols) atomicAdd(&out[c], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n) {
+  const size_t nv = n >> 3;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(b.x, b.y); w.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nv << 3) + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) multi_cast_kernel(const dc_cast_entry* __restrict__ table) {
+  const dc_cast_entry e = table[blockIdx.y];
+  const float* src = e.src;
+  bf16* dst = static_cast<bf16*>(e.dst);
+  const size_t n = e.numel;
+  const size_t nv = n >> 3;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(b.x, b.y); w.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nv << 3) + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT patchify: conv1 (kernel == stride == patch, no bias) as a GEMM over non-overlapping patches —
+// visual_transformer.py:56-59.  dst row = (b, gy, gx), dst col = (c, py, px)  == conv1.weight.view(width, -1).
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, long long sample_stride,
+                                                       bf16* __restrict__ dst, int batch, int res, int patch) {
+  const int G = res / patch;
+  const int kdim = 3 * patch * patch;
+  const int vec_per_row = kdim / 8;
+  const size_t total = static_cast<size_t>(batch) * G * G * vec_per_row;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int kv = static_cast<int>(v % vec_per_row);
+    const size_t row = v / vec_per_row;
+    const int gx = static_cast<int>(row % G);
+    const int gy = static_cast<int>((row / G) % G);
+    const size_t b = row / (static_cast<size_t>(G) * G);
+    const int k = kv * 8;
+    const int c = k / (patch * patch);
+    const int py = (k / patch) % patch;
+    const int px = k % patch;
+    const float* s = img + b * sample_stride + (static_cast<size_t>(c) * res + (gy * patch + py)) * res + gx * patch + px;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(s));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(s) + 1);
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y); w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(bb.x, bb.y); w.w = pack_bf16x2(bb.z, bb.w);
+    *reinterpret_cast<uint4*>(dst + row * kdim + k) = w;
+  }
+}
+
+// visual_transformer.py:60-62: prepend class embedding, add positional embedding.
+__global__ void __launch_bounds__(256) vit_assemble_kernel(const bf16* __restrict__ patch_out,
+                                                           const float* __restrict__ cls, const float* __restrict__ pos,
+                                                           bf16* __restrict__ tokens, int batch, int g2, int width) {
+  const int L = g2 + 1;
+  const int vw = width / 8;
+  const size_t total = static_cast<size_t>(batch) * L * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 8;
+    const size_t tok = v / vw;
+    const int l = static_cast<int>(tok % L);
+    const size_t b = tok / L;
+    float o[8];
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(l) * width + c));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<size_t>(l) * width + c + 4));
+    o[0] = p0.x; o[1] = p0.y; o[2] = p0.z; o[3] = p0.w; o[4] = p1.x; o[5] = p1.y; o[6] = p1.z; o[7] = p1.w;
+    if (l == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + c));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls + c + 4));
+      o[0] += c0.x; o[1] += c0.y; o[2] += c0.z; o[3] += c0.w; o[4] += c1.x; o[5] += c1.y; o[6] += c1.z; o[7] += c1.w;
+    } else {
+      const uint4 u = *reinterpret_cast<const uint4*>(patch_out + (b * g2 + (l - 1)) * width + c);
+      float2 f;
+      f = unpack_bf16x2(u.x); o[0] += f.x; o[1] += f.y;
+      f = unpack_bf16x2(u.y); o[2] += f.x; o[3] += f.y;
+      f = unpack_bf16x2(u.z); o[4] += f.x; o[5] += f.y;
+      f = unpack_bf16x2(u.w); o[6] += f.x; o[7] += f.y;
+    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(tokens + tok * width + c) = w;
+  }
+}
+
+// text_transformer.py:188-190: token embedding gather + positional embedding.
+__global__ void __launch_bounds__(256) text_embed_kernel(const long long* __restrict__ ids,
+                                                         const float* __restrict__ table, const float* __restrict__ pos,
+                                                         bf16* __restrict__ x, int batch, int L, int width) {
+  const int vw = width / 8;
+  const size_t total = static_cast<size_t>(batch) * L * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 8;
+    const size_t tok = v / vw;
+    const int l = static_cast<int>(tok % L);
+    const long long id = ids[tok];
+    const float* t = table + static_cast<size_t>(id) * width + c;
+    const float* p = pos + static_cast<size_t>(l) * width + c;
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(t));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(t) + 1);
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    uint4 w;
+    w.x = pack_bf16x2(t0.x + p0.x, t0.y + p0.y); w.y = pack_bf16x2(t0.z + p0.z, t0.w + p0.w);
+    w.z = pack_bf16x2(t1.x + p1.x, t1.y + p1.y); w.w = pack_bf16x2(t1.z + p1.z, t1.w + p1.w);
+    *reinterpret_cast<uint4*>(x + tok * width + c) = w;
+  }
+}
+
+// Embedding backward: scatter-add into the dense fp32 table gradient with vector reductions.
+__global__ void __launch_bounds__(256) text_embed_bwd_kernel(const long long* __restrict__ ids,
+                                                             const bf16* __restrict__ dx, float* __restrict__ dtable,
+                                                             int batch, int L, int width) {
+  const int vw = width / 8;
+  const size_t total = static_cast<size_t>(batch) * L * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 8;
+    const size_t tok = v / vw;
+    const long long id = ids[tok];
+    const uint4 u = *reinterpret_cast<const uint4*>(dx + tok * width + c);
+    const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+    float* d = dtable + static_cast<size_t>(id) * width + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(f0.x), "f"(f0.y), "f"(f1.x), "f"(f1.y)
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(f2.x), "f"(f2.y), "f"(f3.x),
+                 "f"(f3.y)
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const bf16* __restrict__ src, const int* __restrict__ idx,
+                                                          bf16* __restrict__ dst, int n, int width, int scatter) {
+  const int vw = width / 8;
+  const size_t total = static_cast<size_t>(n) * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 8;
+    const size_t i = v / vw;
+    const size_t r = static_cast<size_t>(idx[i]);
+    if (!scatter)
+      *reinterpret_cast<uint4*>(dst + i * width + c) = *reinterpret_cast<const uint4*>(src + r * width + c);
+    else
+      *reinterpret_cast<uint4*>(dst + r * width + c) = *reinterpret_cast<const uint4*>(src + i * width + c);
+  }
+}
+
+// text_transformer.py:203: the EOT token has the highest id in each sequence -> argmax position.
+__global__ void eot_index_kernel(const long long* __restrict__ ids, int* __restrict__ eot, int batch, int L) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= batch) return;
+  long long best = -1;
+  int bi = 0;
+  for (int l = lane; l < L; l += 32) {
+    const long long v = ids[static_cast<size_t>(b) * L + l];
+    if (v > best) { best = v; bi = l; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) eot[b] = b * L + bi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// clip.py:129-130: y = x / (||x|| + eps); one warp per row.
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ y,
+                                                         float* __restrict__ inv_out, int n, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const float* xr = x + static_cast<size_t>(row) * dim;
+  float s = 0.f;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float inv = 1.0f / (sqrtf(warp_sum(s)) + eps);
+  if (lane == 0 && inv_out) inv_out[row] = inv;
+  bf16* yr = y + static_cast<size_t>(row) * dim;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    uint2 w;
+    w.x = pack_bf16x2(v.x * inv, v.y * inv);
+    w.y = pack_bf16x2(v.z * inv, v.w * inv);
+    *reinterpret_cast<uint2*>(yr + c) = w;
+  }
+}
+
+// dx = inv * dy - x * <dy, x> * inv^2 / r,  r = ||x||, inv = 1/(r + eps).
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         float* __restrict__ dx, int n, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const float* xr = x + static_cast<size_t>(row) * dim;
+  const float* dr = dy + static_cast<size_t>(row) * dim;
+  float s = 0.f, d = 0.f;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(dr + c);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    d += v.x * g.x + v.y * g.y + v.z * g.z + v.w * g.w;
+  }
+  const float r = sqrtf(warp_sum(s));
+  d = warp_sum(d);
+  const float inv = 1.0f / (r + eps);
+  const float k = d * inv * inv / fmaxf(r, 1e-30f);
+  float* o = dx + static_cast<size_t>(row) * dim;
+  for (int c = lane * 4; c < dim; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(dr + c);
+    *reinterpret_cast<float4*>(o + c) =
+        make_float4(inv * g.x - k * v.x, inv * g.y - k * v.y, inv * g.z - k * v.z, inv * g.w - k * v.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ClipInfoCELoss on one [rows, cols] logit strip (loss_functions/loss.py:40-50) fused with
+// accuracy top-1/top-5 (utils/misc.py:415-428).  One block per row; the row (<= 16 KiB) is re-read
+// from L1/L2, never re-fetched from HBM.
+__device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float r = s_red[0];
+  for (int i = 1; i < (blockDim.x >> 5); ++i) r = is_max ? fmaxf(r, s_red[i]) : r + s_red[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
+                                                     int label0, float* __restrict__ loss_sum, int* __restrict__ top1,
+                                                     int* __restrict__ top5, float* __restrict__ lse_out) {
+  __shared__ float s_red[8];
+  const int row = blockIdx.x;
+  const float* z = logits + static_cast<size_t>(row) * ld;
+  const int label = label0 + row;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, z[c]);
+  m = block_reduce(m, s_red, true);
+  const float zl = z[label];
+  float s = 0.f, gt = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = z[c];
+    s += __expf(v - m);
+    gt += (v > zl) ? 1.f : 0.f;
+  }
+  s = block_reduce(s, s_red, false);
+  gt = block_reduce(gt, s_red, false);
+  if (threadIdx.x == 0) {
+    const float lse = m + __logf(s);
+    if (lse_out) lse_out[row] = lse;
+    atomicAdd(loss_sum, lse - zl);
+    if (top1 && gt < 0.5f) atomicAdd(top1, 1);
+    if (top5 && gt < 4.5f) atomicAdd(top5, 1);
+  }
+}
+
+// dlogits = (gscale_host * *gscale_dev) * (softmax(row) - onehot(label)); bf16 or fp32 output
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
+                                                     int label0, const float* __restrict__ lse,
+                                                     const float* __restrict__ gscale_dev, float gscale_host,
+                                                     void* __restrict__ dl, int lddl) {
+  const int row = blockIdx.x;
+  const float* z = logits + static_cast<size_t>(row) * ld;
+  const int label = label0 + row;
+  const float l = lse[row];
+  const float gs = gscale_host * (gscale_dev ? *gscale_dev : 1.0f);
+  for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
+    const float2 v = *reinterpret_cast<const float2*>(z + c);
+    float a = __expf(v.x - l), b = __expf(v.y - l);
+    if (c == label) a -= 1.f;
+    if (c + 1 == label) b -= 1.f;
+    if (OUT_F32)
+      *reinterpret_cast<float2*>(static_cast<float*>(dl) + static_cast<size_t>(row) * lddl + c) = make_float2(gs * a, gs * b);
+    else
+      *reinterpret_cast<uint32_t*>(static_cast<bf16*>(dl) + static_cast<size_t>(row) * lddl + c) = pack_bf16x2(gs * a, gs * b);
+  }
+}
+
+// out += sum_i a[i] * b[i]   (fp32; d logit_scale = sum dlogits * logits / s)
+__global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                  float* __restrict__ out) {
+  __shared__ float s_red[8];
+  float acc = 0.f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) acc += a[i] * b[i];
+  acc = block_reduce(acc, s_red, false);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+static inline int grid_for(size_t work_items, int threads, int per_sm) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(sm_count()) * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace dc
+
+using namespace dc;
+
+extern "C" {
+
+int dc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int rows, int width, float eps, dc_stream_t stream) {
+  if (rows <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 8);
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* yp = static_cast<bf16*>(y);
+  switch (width) {
+    case 256: ln_fwd_kernel<1><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, eps); break;
+    case 512: ln_fwd_kernel<2><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, eps); break;
+    case 768: ln_fwd_kernel<3><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, eps); break;
+    case 1024: ln_fwd_kernel<4><<<grid, 256, 0, st>>>(xp, gamma, beta, yp, mean, rstd, rows, eps); break;
+    default: return set_error("layernorm: width must be 256, 512, 768 or 1024");
+  }
+  DC_CHECK_LAUNCH("layernorm_fwd");
+  return 0;
+}
+
+int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int width,
+                     dc_stream_t stream) {
+  if (rows <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 4);
+  const bf16* dyp = static_cast<const bf16*>(dy);
+  const bf16* xp = static_cast<const bf16*>(x);
+  const bf16* rp = static_cast<const bf16*>(dres);
+  bf16* dxp = static_cast<bf16*>(dx);
+  switch (width) {
+    case 256: ln_bwd_kernel<1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
+    case 512: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
+    case 768: ln_bwd_kernel<3><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
+    case 1024: ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
+    default: return set_error("layernorm: width must be 256, 512, 768 or 1024");
+  }
+  DC_CHECK_LAUNCH("layernorm_bwd");
+  return 0;
+}
+
+int dc_colsum_bf16(const void* x, int ldx, float* out, int rows, int cols, dc_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if ((cols & 7) || (ldx & 7)) return set_error("colsum: cols and ldx must be multiples of 8");
+  dim3 grid((cols + 63) / 64, (rows + COLSUM_ROWS - 1) / COLSUM_ROWS);
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x), ldx, out, rows, cols);
+  DC_CHECK_LAUNCH("colsum");
+  return 0;
+}
+
+int dc_cast_f32_bf16(const float* src, void* dst, size_t n, dc_stream_t stream) {
+  if (n == 0) return 0;
+  cast_kernel<<<grid_for(n / 8 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<bf16*>(dst), n);
+  DC_CHECK_LAUNCH("cast");
+  return 0;
+}
+
+int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsigned long long max_numel,
+                           dc_stream_t stream) {
+  if (n_tensors <= 0) return 0;
+  int bx = static_cast<int>((max_numel / 8 + 255) / 256);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_tensors);
+  multi_cast_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev);
+  DC_CHECK_LAUNCH("multi_cast");
+  return 0;
+}
+
+int dc_patchify(const float* images, long long sample_stride, void* patches, int batch, int res, int patch,
+                dc_stream_t stream) {
+  if (patch % 8 || res % patch) return set_error("patchify: patch must be a multiple of 8 and divide res");
+  const size_t total = static_cast<size_t>(batch) * (res / patch) * (res / patch) * (3 * patch * patch / 8);
+  patchify_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, sample_stride, static_cast<bf16*>(patches), batch, res, patch);
+  DC_CHECK_LAUNCH("patchify");
+  return 0;
+}
+
+int dc_vit_assemble(const void* patch_out, const float* cls, const float* pos, void* tokens, int batch, int g2,
+                    int width, dc_stream_t stream) {
+  const size_t total = static_cast<size_t>(batch) * (g2 + 1) * (width / 8);
+  vit_assemble_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(patch_out), cls, pos, static_cast<bf16*>(tokens), batch, g2, width);
+  DC_CHECK_LAUNCH("vit_assemble");
+  return 0;
+}
+
+int dc_text_embed(const long long* ids, const float* table, const float* pos, void* x, int batch, int L, int width,
+                  dc_stream_t stream) {
+  const size_t total = static_cast<size_t>(batch) * L * (width / 8);
+  text_embed_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, table, pos, static_cast<bf16*>(x), batch, L, width);
+  DC_CHECK_LAUNCH("text_embed");
+  return 0;
+}
+
+int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, int batch, int L, int width,
+                      dc_stream_t stream) {
+  const size_t total = static_cast<size_t>(batch) * L * (width / 8);
+  if (dtable != nullptr) {
+    text_embed_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, static_cast<const bf16*>(dx), dtable, batch, L, width);
+    DC_CHECK_LAUNCH("text_embed_bwd");
+  }
+  if (dpos != nullptr) return dc_colsum_bf16(dx, L * width, dpos, batch, L * width, stream);
+  return 0;
+}
+
+int dc_gather_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream) {
+  if (n <= 0) return 0;
+  const size_t total = static_cast<size_t>(n) * (width / 8);
+  gather_rows_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(src), idx, static_cast<bf16*>(dst), n, width, 0);
+  DC_CHECK_LAUNCH("gather_rows");
+  return 0;
+}
+
+int dc_scatter_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream) {
+  if (n <= 0) return 0;
+  const size_t total = static_cast<size_t>(n) * (width / 8);
+  gather_rows_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(src), idx, static_cast<bf16*>(dst), n, width, 1);
+  DC_CHECK_LAUNCH("scatter_rows");
+  return 0;
+}
+
+int dc_eot_index(const long long* ids, int* eot, int batch, int L, dc_stream_t stream) {
+  if (batch <= 0) return 0;
+  eot_index_kernel<<<(batch * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ids, eot, batch, L);
+  DC_CHECK_LAUNCH("eot_index");
+  return 0;
+}
+
+int dc_l2norm_fwd(const float* x, void* y, float* inv, int n, int dim, float eps, dc_stream_t stream) {
+  if (n <= 0) return 0;
+  if (dim & 3) return set_error("l2norm: dim must be a multiple of 4");
+  l2norm_fwd_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(y), inv, n,
+                                                                                     dim, eps);
+  DC_CHECK_LAUNCH("l2norm_fwd");
+  return 0;
+}
+
+int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, float eps, dc_stream_t stream) {
+  if (n <= 0) return 0;
+  if (dim & 3) return set_error("l2norm: dim must be a multiple of 4");
+  l2norm_bwd_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, x, dx, n, dim, eps);
+  DC_CHECK_LAUNCH("l2norm_bwd");
+  return 0;
+}
+
+int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, float* loss_sum, int* top1,
+                    int* top5, float* lse_out, dc_stream_t stream) {
+  if (rows <= 0) return 0;
+  if (label0 < 0 || label0 + rows > cols) return set_error("ce_strip: labels out of range");
+  ce_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, loss_sum, top1, top5,
+                                                                 lse_out);
+  DC_CHECK_LAUNCH("ce_strip_fwd");
+  return 0;
+}
+
+int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const float* lse,
+                    const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
+                    dc_stream_t stream) {
+  if (rows <= 0) return 0;
+  if ((cols & 1) || (ld & 1) || (lddl & 1)) return set_error("ce_strip: cols/ld must be even");
+  if (out_f32)
+    ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, lse,
+                                                                         gscale_dev, gscale_host, dlogits, lddl);
+  else
+    ce_bwd_kernel<false><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, lse,
+                                                                          gscale_dev, gscale_host, dlogits, lddl);
+  DC_CHECK_LAUNCH("ce_strip_bwd");
+  return 0;
+}
+
+int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t stream) {
+  if (n == 0) return 0;
+  dot_kernel<<<grid_for(n, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, out);
+  DC_CHECK_LAUNCH("dot");
+  return 0;
+}
+
+}  // extern "C"

@@ -29,7 +29,7 @@ def lib_for(t):
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1.0, bias=None, aux=None, out=None,
-         out2=None, splits=0, block_n=0):
+         out2=None, splits=0, block_n=0, alpha_dev=None):
     """out[M,N] (op)= epilogue(alpha * sum_k A(m,k) B(n,k)).
 
     a: [M,K] (or [K,M] if a_mn_major), b: [N,K] (or [K,N] if b_mn_major); both bf16, last dim contiguous.
@@ -69,7 +69,97 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1
         assert aux.dtype == torch.bfloat16 and aux.stride(-1) == 1
         args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
     args.splits, args.block_n = splits, block_n
+    if alpha_dev is not None:
+        assert alpha_dev.dtype == torch.float32 and alpha_dev.is_cuda
+        args.alpha_dev = alpha_dev.data_ptr()
     _lib.check(lib.dc_gemm_bf16(ctypes.byref(args), _stream()), "dc_gemm_bf16")
     if epilogue == EPI_BF16_GELU:
         return out, out2
+    return out
+
+
+# ------------------------------------------------------------------ op-level wrappers (tests, tools)
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    lib = lib_for(x)
+    rows, width = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _lib.check(lib.dc_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, width, eps,
+                                    _stream()), "dc_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
+    lib = lib_for(x)
+    rows, width = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(width, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros(width, device=x.device, dtype=torch.float32)
+    _lib.check(lib.dc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
+                                    _ptr(dgamma), _ptr(dbeta), rows, width, _stream()), "dc_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+def colsum(x, out=None):
+    lib = lib_for(x)
+    rows, cols = x.shape
+    if out is None:
+        out = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    _lib.check(lib.dc_colsum_bf16(_ptr(x), x.stride(0), _ptr(out), rows, cols, _stream()), "dc_colsum_bf16")
+    return out
+
+
+def attention_fwd(qkv, batch, L, heads, causal):
+    lib = lib_for(qkv)
+    D = heads * 64
+    out = torch.empty(batch * L, D, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(batch * heads * L, device=qkv.device, dtype=torch.float32)
+    _lib.check(lib.dc_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), batch, L, heads, int(causal), _stream()),
+               "dc_attention_fwd")
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, batch, L, heads, causal):
+    lib = lib_for(qkv)
+    dqkv = torch.empty_like(qkv)
+    _lib.check(lib.dc_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), batch, L, heads,
+                                    int(causal), _stream()), "dc_attention_bwd")
+    return dqkv
+
+
+def patchify(images, patch):
+    lib = lib_for(images)
+    B, C, R, _ = images.shape
+    g = R // patch
+    out = torch.empty(B * g * g, 3 * patch * patch, device=images.device, dtype=torch.bfloat16)
+    _lib.check(lib.dc_patchify(_ptr(images), images.stride(0), _ptr(out), B, R, patch, _stream()), "dc_patchify")
+    return out
+
+
+def text_embed(ids, table, pos):
+    lib = lib_for(table)
+    B, L = ids.shape
+    W = table.shape[1]
+    x = torch.empty(B * L, W, device=table.device, dtype=torch.bfloat16)
+    _lib.check(lib.dc_text_embed(_ptr(ids), _ptr(table), _ptr(pos), _ptr(x), B, L, W, _stream()), "dc_text_embed")
+    return x
+
+
+def text_embed_bwd(ids, dx, vocab):
+    lib = lib_for(dx)
+    B, L = ids.shape
+    W = dx.shape[1]
+    dtable = torch.zeros(vocab, W, device=dx.device, dtype=torch.float32)
+    dpos = torch.zeros(L, W, device=dx.device, dtype=torch.float32)
+    _lib.check(lib.dc_text_embed_bwd(_ptr(ids), _ptr(dx), _ptr(dtable), _ptr(dpos), B, L, W, _stream()),
+               "dc_text_embed_bwd")
+    return dtable, dpos
+
+
+def eot_index(ids):
+    lib = lib_for(ids)
+    B, L = ids.shape
+    out = torch.empty(B, device=ids.device, dtype=torch.int32)
+    _lib.check(lib.dc_eot_index(_ptr(ids), _ptr(out), B, L, _stream()), "dc_eot_index")
     return out

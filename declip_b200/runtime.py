@@ -1,0 +1,238 @@
+"""Host-side runtime of one encoder tower: bf16 weight shadows, flat fp32 gradient buffer, pointer
+tables and workspace for the C++ executors (csrc/encoder.cu), plus the autograd bridge.
+
+PyTorch's role here is plumbing only — it owns device memory (caching allocator), the current
+stream and autograd bookkeeping.  All arithmetic is in declip_b200/_C.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CastEntry, TowerCfg
+
+_PTR = ctypes.c_void_p
+
+
+def _stream():
+    return _PTR(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr_array(ptrs):
+    arr = (_PTR * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+LAYER_BF16 = ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight")
+LAYER_F32 = ("ln_1.weight", "ln_1.bias", "attn.in_proj_bias", "attn.out_proj.bias", "ln_2.weight", "ln_2.bias",
+             "mlp.c_fc.bias", "mlp.c_proj.bias")
+LAYER_GRADS = ("attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias", "ln_1.weight",
+               "ln_1.bias", "mlp.c_fc.weight", "mlp.c_fc.bias", "mlp.c_proj.weight", "mlp.c_proj.bias", "ln_2.weight",
+               "ln_2.bias")
+VIT_BF16 = ("conv1.weight", "proj")
+VIT_F32 = ("class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight", "ln_post.bias")
+VIT_GRADS = ("class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias", "ln_post.weight", "ln_post.bias",
+             "proj")
+TEXT_BF16 = ("text_projection.weight",)
+TEXT_F32 = ("token_embedding.weight", "positional_embedding", "ln_final.weight", "ln_final.bias", "text_projection.bias")
+TEXT_GRADS = ("token_embedding.weight", "positional_embedding", "ln_final.weight", "ln_final.bias",
+              "text_projection.weight", "text_projection.bias")
+
+
+class TowerRuntime:
+    """Per-module state for dc_{vit,text}_{forward,backward}.  `kind` is 'vit' or 'text'."""
+
+    def __init__(self, kind, module, layers, width, heads, seq_len, embed_dim, res=0, patch=0, vocab=0):
+        self.kind = kind
+        self.module = module
+        self.layers, self.width, self.heads, self.seq_len, self.embed_dim = layers, width, heads, seq_len, embed_dim
+        self.res, self.patch, self.vocab = res, patch, vocab
+        pre = "transformer.resblocks.%d."
+        extra_bf16, extra_f32, extra_grads = (VIT_BF16, VIT_F32, VIT_GRADS) if kind == "vit" else (TEXT_BF16, TEXT_F32,
+                                                                                                    TEXT_GRADS)
+        self.bf16_names = [pre % l + n for l in range(layers) for n in LAYER_BF16] + list(extra_bf16)
+        self.f32_names = [pre % l + n for l in range(layers) for n in LAYER_F32] + list(extra_f32)
+        self.grad_names = [pre % l + n for l in range(layers) for n in LAYER_GRADS] + list(extra_grads)
+        self._key = None          # (device, tuple of param data_ptrs)
+        self._versions = None
+        self.grad_flat = None
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def _params(self):
+        return dict(self.module.named_parameters())
+
+    def _prepare(self, params):
+        dev = params[self.f32_names[0]].device
+        key = (dev, tuple(params[n].data_ptr() for n in self.bf16_names + self.f32_names))
+        if key == self._key:
+            return
+        for n in self.bf16_names + self.f32_names:
+            p = params[n]
+            if p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda:
+                raise RuntimeError("declip_b200: parameter %s must be a contiguous fp32 CUDA tensor (master weights "
+                                   "stay fp32; bf16 shadows are internal)" % n)
+        self.lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        # bf16 shadows of the GEMM weights, one flat buffer
+        offs, total = [], 0
+        for n in self.bf16_names:
+            offs.append(total)
+            total += (params[n].numel() + 127) // 128 * 128
+        self.shadow = torch.empty(total, device=dev, dtype=torch.bfloat16)
+        entries = (CastEntry * len(self.bf16_names))()
+        max_numel = 0
+        for i, n in enumerate(self.bf16_names):
+            entries[i].src = params[n].data_ptr()
+            entries[i].dst = self.shadow.data_ptr() + 2 * offs[i]
+            entries[i].numel = params[n].numel()
+            max_numel = max(max_numel, params[n].numel())
+        raw = bytes(entries)
+        self.cast_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.cast_n, self.cast_max = len(self.bf16_names), max_numel
+        self.w_bf16 = _ptr_array([self.shadow.data_ptr() + 2 * o for o in offs])
+        self.w_f32 = _ptr_array([params[n].data_ptr() for n in self.f32_names])
+        # flat fp32 gradient buffer in the executor's table order
+        goffs, gtotal = [], 0
+        for n in self.grad_names:
+            goffs.append(gtotal)
+            gtotal += (params[n].numel() + 63) // 64 * 64
+        self.grad_flat = torch.zeros(gtotal, device=dev, dtype=torch.float32)
+        self.grad_offs = goffs
+        self.grad_ptrs = _ptr_array([self.grad_flat.data_ptr() + 4 * o for o in goffs])
+        self._key = key
+        self._versions = None
+
+    def refresh_shadows(self, params):
+        """fp32 master -> bf16 shadow for every GEMM weight (one launch); skipped when nothing changed."""
+        versions = tuple(params[n]._version for n in self.bf16_names)
+        if versions == self._versions:
+            return
+        _lib.check(self.lib.dc_multi_cast_f32_bf16(_PTR(self.cast_table.data_ptr()), self.cast_n, self.cast_max, _stream()),
+                   "dc_multi_cast_f32_bf16")
+        self._versions = versions
+
+    def cfg(self, batch):
+        c = TowerCfg()
+        c.layers, c.width, c.heads, c.seq_len = self.layers, self.width, self.heads, self.seq_len
+        c.causal = 1 if self.kind == "text" else 0
+        c.batch, c.embed_dim, c.res, c.patch, c.vocab = batch, self.embed_dim, self.res, self.patch, self.vocab
+        return c
+
+    def workspace(self, cfg, dev):
+        """A fresh workspace per forward (torch's caching allocator makes this cheap): a module may be run
+        several times before backward (DeCLIP encodes two image views, declip.py:231-232)."""
+        nbytes = self.lib.dc_tower_workspace_bytes(ctypes.byref(cfg))
+        if nbytes == 0:
+            raise RuntimeError("declip_b200: bad tower config: " + _lib.last_error())
+        return torch.empty(nbytes, device=dev, dtype=torch.uint8)
+
+    # ------------------------------------------------------------------ executors
+    def forward(self, inp, params):
+        self._prepare(params)
+        self.refresh_shadows(params)
+        batch = inp.shape[0]
+        cfg = self.cfg(batch)
+        ws = self.workspace(cfg, inp.device)
+        feats = torch.empty(batch, self.embed_dim, device=inp.device, dtype=torch.float32)
+        if self.kind == "vit":
+            if inp.dtype != torch.float32 or inp.stride(3) != 1 or inp.stride(2) != self.res or inp.stride(1) != self.res ** 2:
+                inp = inp.float().contiguous()
+            _lib.check(self.lib.dc_vit_forward(ctypes.byref(cfg), _PTR(inp.data_ptr()), inp.stride(0), self.w_bf16,
+                                               self.w_f32, _PTR(ws.data_ptr()), _PTR(feats.data_ptr()), _stream()),
+                       "dc_vit_forward")
+        else:
+            if inp.dtype != torch.int64 or not inp.is_contiguous():
+                inp = inp.long().contiguous()
+            _lib.check(self.lib.dc_text_forward(ctypes.byref(cfg), _PTR(inp.data_ptr()), self.w_bf16, self.w_f32,
+                                                _PTR(ws.data_ptr()), _PTR(feats.data_ptr()), _stream()),
+                       "dc_text_forward")
+        return feats, inp, cfg, ws
+
+    def backward(self, cfg, inp, ws, dfeats, params):
+        """Accumulates parameter gradients straight into `p.grad` (views of one flat fp32 buffer per tower, the
+        DDP/"main_grad" pattern), so the gradient all-reduce is a single NCCL call per tower and a module that is
+        run several times per step accumulates correctly.  Ownership rules per parameter:
+          p.grad is None            -> zero its slice, attach the slice as p.grad
+          p.grad is already a slice -> accumulate in place (also covers zero_grad(set_to_none=False))
+          p.grad is a foreign tensor-> compute into a private buffer and add."""
+        views = getattr(self, "_views", None)
+        if views is None or self._views_key is not self.grad_flat:
+            views = [self.grad_flat[o:o + params[n].numel()].view_as(params[n])
+                     for n, o in zip(self.grad_names, self.grad_offs)]
+            self._views, self._views_key = views, self.grad_flat
+        foreign = []
+        all_fresh = True
+        for n, v in zip(self.grad_names, views):
+            p = params[n]
+            if not p.requires_grad:
+                continue
+            g = p.grad
+            if g is None:
+                continue
+            all_fresh = False
+            if g.data_ptr() != v.data_ptr() or g.dtype != torch.float32:
+                foreign.append(n)
+        ptrs = self.grad_ptrs
+        tmp = None
+        if foreign:
+            tmp = torch.zeros_like(self.grad_flat)
+            ptrs = _ptr_array([tmp.data_ptr() + 4 * o for o in self.grad_offs])
+        elif all_fresh:
+            self.grad_flat.zero_()
+        else:
+            for n, v in zip(self.grad_names, views):
+                if params[n].requires_grad and params[n].grad is None:
+                    v.zero_()
+        dfeats = dfeats.float().contiguous()
+        if self.kind == "vit":
+            _lib.check(self.lib.dc_vit_backward(ctypes.byref(cfg), _PTR(dfeats.data_ptr()), self.w_bf16, self.w_f32, ptrs,
+                                                _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
+        else:
+            _lib.check(self.lib.dc_text_backward(ctypes.byref(cfg), _PTR(inp.data_ptr()), _PTR(dfeats.data_ptr()),
+                                                 self.w_bf16, self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()),
+                       "dc_text_backward")
+        if tmp is not None:
+            for n, o in zip(self.grad_names, self.grad_offs):
+                p = params[n]
+                if not p.requires_grad:
+                    continue
+                t = tmp[o:o + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = t.clone()
+                else:
+                    p.grad.add_(t)
+        else:
+            for n, v in zip(self.grad_names, views):
+                p = params[n]
+                if p.requires_grad and p.grad is None:
+                    p.grad = v
+
+
+class _TowerFunction(torch.autograd.Function):
+    """features = tower(inp; params).  One C-ABI call forward, one backward.  Parameter gradients are written
+    into p.grad by the runtime (see TowerRuntime.backward); autograd only carries d(features)."""
+
+    @staticmethod
+    def forward(ctx, rt, inp, anchor):
+        params = rt._params()
+        feats, inp_used, cfg, ws = rt.forward(inp, params)
+        ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params = rt, cfg, inp_used, ws, params
+        return feats
+
+    @staticmethod
+    def backward(ctx, dfeats):
+        ctx.rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params)
+        ctx.ws = None
+        return None, None, None
+
+
+def run_tower(rt, inp):
+    """Run the tower through autograd (training) or directly (no_grad / eval).  `anchor` is any trainable
+    parameter: it makes the output require grad so backward is invoked."""
+    params = rt._params()
+    if torch.is_grad_enabled():
+        anchor = next((p for p in params.values() if p.requires_grad), None)
+        if anchor is not None:
+            return _TowerFunction.apply(rt, inp, anchor)
+    return rt.forward(inp, params)[0]

@@ -65,6 +65,8 @@ typedef struct {
   const void* aux; int ldaux; /* bf16 [M,N] or NULL */
   int splits;                 /* split-K factor, 0 = auto (only DC_EPI_F32_ATOMIC may split) */
   int block_n;                /* 0 = auto, else 128 or 256 */
+  const float* alpha_dev;     /* optional DEVICE scalar multiplied into alpha (e.g. the clamped exp(logit_scale),
+                                 clip.py:133-134) so no host sync is needed; NULL = 1 */
 } dc_gemm_args;
 int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
 
@@ -123,16 +125,22 @@ int dc_eot_index(const long long* ids, int* eot, int batch, int L, dc_stream_t s
 /* ------------------------------------------------------------------ contrastive head
  * clip.py:129-130: y = x / (||x|| + eps) row-wise; x fp32 [n,dim] -> y bf16, inv fp32 [n] = 1/(||x||+eps). */
 int dc_l2norm_fwd(const float* x, void* y, float* inv, int n, int dim, float eps, dc_stream_t stream);
-/* dx(fp32) = inv * (dy - yhat * <dy, yhat> * c) with c = ||x||*inv (==1 for eps=0); dy fp32, yhat bf16. */
-int dc_l2norm_bwd(const float* dy, const void* y, const float* inv, float* dx, int n, int dim, float eps,
-                  dc_stream_t stream);
-/* loss.py:40-50 (ClipInfoCELoss) on one logit strip, fused with its backward and with
- * misc.py:415-428 (accuracy top-1/top-5):  logits fp32 [rows,cols], label[r] = label0 + r.
- *   loss_sum  += sum_r (lse_r - logit[r,label_r])           (fp32 atomic)
- *   top1/top5 += #{r : rank of the label among the row < 1 / < 5}
- *   dlogits (bf16 [rows,cols], may be NULL) = gscale * (softmax(row) - onehot(label))      */
-int dc_ce_strip(const float* logits, int ld, int rows, int cols, int label0, float gscale, float* loss_sum,
-                int* top1, int* top5, void* dlogits, int lddl, float* lse_out, dc_stream_t stream);
+/* dx(fp32) = inv*dy - x * <dy,x> * inv^2 / ||x||  with inv = 1/(||x|| + eps); dy, x fp32 [n,dim]. */
+int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, float eps, dc_stream_t stream);
+/* loss.py:40-50 (ClipInfoCELoss) on one logit strip, fused with misc.py:415-428 (accuracy top-1/top-5):
+ * logits fp32 [rows,cols] (row stride ld), label[r] = label0 + r.
+ *   *loss_sum += sum_r (lse_r - logit[r,label_r])      (fp32 atomic; caller zeroes and divides by rows)
+ *   *top1/*top5 += #{r : #(logit[r,:] > logit[r,label_r]) < 1 / < 5}   (may be NULL)
+ *   lse_out[r] = log-sum-exp of row r (saved for backward). */
+int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, float* loss_sum, int* top1,
+                    int* top5, float* lse_out, dc_stream_t stream);
+/* dlogits([rows,cols], row stride lddl; bf16, or fp32 when out_f32) =
+ *   gscale_host * (*gscale_dev) * (softmax(row) - onehot(label));  gscale_dev may be NULL (treated as 1). */
+int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const float* lse,
+                    const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
+                    dc_stream_t stream);
+/* *out += sum_i a[i]*b[i]  (fp32; used for d logit_scale = exp(ls)/s * sum dlogits*logits, clip.py:133-141) */
+int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t stream);
 
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.

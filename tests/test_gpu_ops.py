@@ -1,0 +1,179 @@
+"""GPU: each C-ABI kernel against a plain PyTorch fp32 reference of the same op (bf16 I/O tolerance stated
+per test).  Called through ctypes — the same path the product uses."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-20)).item()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (392, 768, 3072), (1000, 2304, 768), (8, 512, 768), (512, 4096, 512),
+                                   (3072, 768, 1544)])
+def test_gemm_majors(cuda_dev, a_mn, b_mn, shape):
+    from declip_b200 import ops
+    M, N, K = shape
+    torch.manual_seed(0)
+    a = (torch.randn((K, M) if a_mn else (M, K), device=cuda_dev) * 0.5).bfloat16()
+    b = (torch.randn((K, N) if b_mn else (N, K), device=cuda_dev) * 0.5).bfloat16()
+    want = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+    for bn in (0, 128, 256):
+        got = ops.gemm(a, b, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), epilogue=ops.EPI_F32, block_n=bn)
+        assert _rel(got, want) < 1e-5, (shape, a_mn, b_mn, bn)     # fp32 accumulate of exact bf16 products
+
+
+def test_gemm_epilogues(cuda_dev):
+    from declip_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 1000, 768, 512
+    a = (torch.randn(M, K, device=cuda_dev) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device=cuda_dev) * 0.5).bfloat16()
+    bias = torch.randn(N, device=cuda_dev)
+    aux = torch.randn(M, N, device=cuda_dev).bfloat16()
+    want = a.float() @ b.float().t()
+    assert _rel(ops.gemm(a, b, bias=bias), want + bias) < 4e-3            # bf16 output rounding
+    h, u = ops.gemm(a, b, bias=bias, epilogue=ops.EPI_BF16_GELU)
+    uu = want + bias
+    assert _rel(u, uu) < 4e-3 and _rel(h, uu * torch.sigmoid(1.702 * uu)) < 4e-3
+    assert _rel(ops.gemm(a, b, bias=bias, aux=aux, epilogue=ops.EPI_BF16_RESID), want + bias + aux.float()) < 4e-3
+    x = aux.float()
+    s = torch.sigmoid(1.702 * x)
+    assert _rel(ops.gemm(a, b, aux=aux, epilogue=ops.EPI_BF16_DGELU), want * (s * (1 + 1.702 * x * (1 - s)))) < 5e-3
+    sc = torch.tensor([2.5], device=cuda_dev)
+    assert _rel(ops.gemm(a, b, epilogue=ops.EPI_F32, alpha_dev=sc), 2.5 * want) < 1e-5
+    acc = torch.ones(N, K, device=cuda_dev)
+    dy = (torch.randn(4096, N, device=cuda_dev) * 0.5).bfloat16()
+    xx = (torch.randn(4096, K, device=cuda_dev) * 0.5).bfloat16()
+    for sp in (0, 1, 5):
+        acc.fill_(1.0)
+        ops.gemm(dy, xx, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC, out=acc, splits=sp)
+        assert _rel(acc, dy.float().t() @ xx.float() + 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("width", [512, 768])
+@pytest.mark.parametrize("rows", [1, 50, 3333])
+def test_layernorm(cuda_dev, width, rows):
+    from declip_b200 import ops
+    torch.manual_seed(2)
+    x = (torch.randn(rows, width, device=cuda_dev) * 2 + 0.3).bfloat16()
+    g = 1 + 0.1 * torch.randn(width, device=cuda_dev)
+    b = 0.1 * torch.randn(width, device=cuda_dev)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (width,), gr, br, 1e-5)
+    assert _rel(y, yr) < 4e-3
+    assert torch.allclose(mean, xr.mean(1), atol=1e-4) and _rel(rstd, 1 / torch.sqrt(xr.var(1, unbiased=False) + 1e-5)) < 1e-4
+    dy = torch.randn(rows, width, device=cuda_dev).bfloat16()
+    dres = torch.randn(rows, width, device=cuda_dev).bfloat16()
+    yr.backward(dy.float())
+    dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd, dres)
+    assert _rel(dx, xr.grad + dres.float()) < 5e-3
+    assert _rel(dg, gr.grad) < 1e-3 and _rel(db, br.grad) < 1e-3
+    dx2, _, _ = ops.layernorm_bwd(dy, x, g, mean, rstd, None)
+    assert _rel(dx2, xr.grad) < 5e-3
+
+
+def test_colsum(cuda_dev):
+    from declip_b200 import ops
+    x = torch.randn(2500, 2304, device=cuda_dev).bfloat16()
+    out = torch.ones(2304, device=cuda_dev)
+    ops.colsum(x, out)
+    assert _rel(out, x.float().sum(0) + 1) < 1e-4
+    # strided view (class-token rows of a [B, L*W] tensor)
+    y = torch.randn(37, 50 * 768, device=cuda_dev).bfloat16()
+    assert _rel(ops.colsum(y[:, :768]), y[:, :768].float().sum(0)) < 1e-4
+
+
+def _ref_attention(qkv, B, L, H, causal):
+    D = H * 64
+    q, k, v = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device=qkv.device).triu_(1)
+    p = torch.softmax(s, -1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * L, D)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("L,H,causal", [(50, 12, False), (77, 8, True), (77, 8, False), (17, 4, True), (64, 2, False),
+                                        (80, 2, True), (1, 2, True)])
+def test_attention(cuda_dev, L, H, causal):
+    from declip_b200 import ops
+    torch.manual_seed(3)
+    B, D = 5, H * 64
+    qkv = torch.randn(B * L, 3 * D, device=cuda_dev).bfloat16()
+    out, lse = ops.attention_fwd(qkv, B, L, H, causal)
+    qr = qkv.float().requires_grad_(True)
+    o_ref, lse_ref = _ref_attention(qr, B, L, H, causal)
+    assert _rel(out, o_ref) < 1e-2                                   # P is rounded to bf16 before P V
+    assert torch.allclose(lse.view(B, H, L), lse_ref, atol=2e-3)
+    dout = torch.randn(B * L, D, device=cuda_dev).bfloat16()
+    o_ref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, causal)
+    assert _rel(dqkv, qr.grad) < 2e-2 and _cos(dqkv, qr.grad) > 0.9995
+
+
+def test_embeddings(cuda_dev):
+    from declip_b200 import ops
+    torch.manual_seed(4)
+    img = torch.randn(3, 3, 224, 224, device=cuda_dev)
+    p = ops.patchify(img, 32)
+    ref = torch.nn.functional.unfold(img, kernel_size=32, stride=32).transpose(1, 2).reshape(3 * 49, 3072)
+    assert torch.equal(p.float(), ref.bfloat16().float())
+    # 6-channel two-view layout (DeCLIP): second view through a channel-offset view
+    img6 = torch.randn(2, 6, 224, 224, device=cuda_dev)
+    p2 = ops.patchify(img6[:, 3:], 32)
+    ref2 = torch.nn.functional.unfold(img6[:, 3:], kernel_size=32, stride=32).transpose(1, 2).reshape(2 * 49, 3072)
+    assert torch.equal(p2.float(), ref2.bfloat16().float())
+    from oracle import synth
+    ids = synth.synth_token_ids(9, seed=5).to(cuda_dev)
+    table = torch.randn(49409, 512, device=cuda_dev)
+    pos = torch.randn(77, 512, device=cuda_dev)
+    x = ops.text_embed(ids, table, pos)
+    assert _rel(x, (table[ids] + pos).reshape(-1, 512)) < 4e-3
+    assert torch.equal(ops.eot_index(ids).long(), torch.arange(9, device=cuda_dev) * 77 + ids.argmax(1))
+    dx = torch.randn(9 * 77, 512, device=cuda_dev).bfloat16()
+    dt, dp = ops.text_embed_bwd(ids, dx, 49409)
+    ref_t = torch.zeros(49409, 512, device=cuda_dev).index_add_(0, ids.reshape(-1), dx.float())
+    assert _rel(dt, ref_t) < 1e-5 and _rel(dp, dx.float().view(9, 77, 512).sum(0)) < 1e-4
+
+
+def test_head_functions(cuda_dev):
+    """ClipLogits + ClipInfoCE against the oracle restatement (clip.py:129-141, loss.py:40-50), incl. the
+    clamped-scale gradient semantics and top-1/top-5."""
+    from declip_b200 import functions as F_
+    from declip_b200.loss_functions import ClipInfoCELoss
+    from oracle import clip_ref
+    torch.manual_seed(5)
+    for ls0 in (math.log(1 / 0.07), 5.5):
+        fi = torch.randn(48, 512, device=cuda_dev, requires_grad=True)
+        ft = torch.randn(48, 512, device=cuda_dev, requires_grad=True)
+        ls = torch.tensor([ls0], device=cuda_dev, requires_grad=True)
+        li, lt = F_.ClipLogits.apply(fi, ft, ls, False, True)
+        crit = ClipInfoCELoss()
+        loss, labels = crit(li, lt)
+        loss.backward()
+        fi_r, ft_r, ls_r = (t.detach().cpu().clone().requires_grad_(True) for t in (fi, ft, ls))
+        li_r, lt_r, _, _ = clip_ref.clip_logits(fi_r, ft_r, ls_r)
+        loss_r, labels_r = clip_ref.clip_info_ce(li_r, lt_r)
+        loss_r.backward()
+        assert _rel(li.cpu(), li_r) < 6e-3 and _rel(lt.cpu(), lt_r) < 6e-3       # bf16 features into the GEMM
+        assert abs(loss.item() - loss_r.item()) < 2e-2
+        assert torch.equal(labels.cpu(), labels_r)
+        assert _cos(fi.grad.cpu(), fi_r.grad) > 0.995 and _cos(ft.grad.cpu(), ft_r.grad) > 0.995
+        assert abs(ls.grad.item() - ls_r.grad.item()) < 0.05 * abs(ls_r.grad.item()) + 1e-3
+        p1, p5 = crit.accuracy()
+        r1, r5 = clip_ref.accuracy(li.detach().cpu(), labels_r)
+        assert abs(p1.item() - r1.item()) < 1e-3 and abs(p5.item() - r5.item()) < 1e-3
