@@ -497,15 +497,23 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
   const int label = label0 + row;
   const float l = lse[row];
   const float gs = gscale_host * (gscale_dev ? *gscale_dev : 1.0f);
+  const bool vec_ok = ((ld | lddl) & 1) == 0;
   for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
-    const float2 v = *reinterpret_cast<const float2*>(z + c);
-    float a = __expf(v.x - l), b = __expf(v.y - l);
+    const bool has2 = c + 1 < cols;
+    float a = __expf(z[c] - l), b = has2 ? __expf(z[c + 1] - l) : 0.f;
     if (c == label) a -= 1.f;
     if (c + 1 == label) b -= 1.f;
-    if (OUT_F32)
-      *reinterpret_cast<float2*>(static_cast<float*>(dl) + static_cast<size_t>(row) * lddl + c) = make_float2(gs * a, gs * b);
-    else
-      *reinterpret_cast<uint32_t*>(static_cast<bf16*>(dl) + static_cast<size_t>(row) * lddl + c) = pack_bf16x2(gs * a, gs * b);
+    a *= gs;
+    b *= gs;
+    if (OUT_F32) {
+      float* d = static_cast<float*>(dl) + static_cast<size_t>(row) * lddl + c;
+      if (has2 && vec_ok) *reinterpret_cast<float2*>(d) = make_float2(a, b);
+      else { d[0] = a; if (has2) d[1] = b; }
+    } else {
+      bf16* d = static_cast<bf16*>(dl) + static_cast<size_t>(row) * lddl + c;
+      if (has2 && vec_ok) *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(a, b);
+      else { d[0] = __float2bfloat16(a); if (has2) d[1] = __float2bfloat16(b); }
+    }
   }
 }
 
@@ -697,7 +705,6 @@ int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0,
                     const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
                     dc_stream_t stream) {
   if (rows <= 0) return 0;
-  if ((cols & 1) || (ld & 1) || (lddl & 1)) return set_error("ce_strip: cols/ld must be even");
   if (out_f32)
     ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, lse,
                                                                          gscale_dev, gscale_host, dlogits, lddl);

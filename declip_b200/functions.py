@@ -25,10 +25,15 @@ def dist_info():
     return 0, 1
 
 
-def l2norm_fwd(x, eps):
+def l2norm_fwd(x, eps, rows_pad=None):
+    """y = x / (||x|| + eps) in bf16; optionally zero-padded to `rows_pad` rows (TMA needs 16-byte row strides
+    on the gathered dimension, so odd batch sizes are padded internally)."""
     lib = ops.lib_for(x)
     n, d = x.shape
-    y = torch.empty(n, d, device=x.device, dtype=torch.bfloat16)
+    if rows_pad is not None and rows_pad != n:
+        y = torch.zeros(rows_pad, d, device=x.device, dtype=torch.bfloat16)
+    else:
+        y = torch.empty(n, d, device=x.device, dtype=torch.bfloat16)
     _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), _PTR(y.data_ptr()), None, n, d, eps, _stream()), "dc_l2norm_fwd")
     return y
 
@@ -66,40 +71,55 @@ class ClipLogits(torch.autograd.Function):
     def forward(ctx, image_features, text_features, logit_scale, gather, clamp):
         image_features = image_features.float().contiguous()
         text_features = text_features.float().contiguous()
-        i_n = l2norm_fwd(image_features, 0.0)          # clip.py:129
-        t_n = l2norm_fwd(text_features, 1e-10)         # clip.py:130
+        b, e = image_features.shape
         rank, world = dist_info()
         gather = bool(gather) and world > 1
+        if gather and b % 8:
+            raise RuntimeError("declip_b200: per-rank batch must be a multiple of 8 when features are all-gathered")
+        bp = (b + 7) // 8 * 8
+        i_n = l2norm_fwd(image_features, 0.0, bp)      # clip.py:129
+        t_n = l2norm_fwd(text_features, 1e-10, bp)     # clip.py:130
         if gather:
-            b, e = i_n.shape
             both = torch.cat([i_n, t_n], dim=1)                       # one collective for both towers
             allb = torch.empty(world * b, 2 * e, device=i_n.device, dtype=torch.bfloat16)
             dist.all_gather_into_tensor(allb, both)
             i_all, t_all = allb[:, :e], allb[:, e:]
         else:
             i_all, t_all = i_n, t_n
+        n_pad = i_all.shape[0]
+        n = world * b if gather else b
         s_raw = logit_scale.detach().float().exp().reshape(1)
         s_used = torch.clamp(s_raw, max=100.0) if clamp else s_raw           # clip.py:133-134
         # the scale stays on the device (alpha_dev): no host sync in the step
-        li = ops.gemm(i_n, t_all, epilogue=ops.EPI_F32, alpha_dev=s_used)   # [b,N] = s * I_loc T_all^T   clip.py:140
-        lt = ops.gemm(t_n, i_all, epilogue=ops.EPI_F32, alpha_dev=s_used)   # [b,N] = s * T_loc I_all^T   clip.py:141
+        li = ops.gemm(i_n[:b], t_all, epilogue=ops.EPI_F32, alpha_dev=s_used)   # [b,N] = s I_loc T_all^T  clip.py:140
+        lt = ops.gemm(t_n[:b], i_all, epilogue=ops.EPI_F32, alpha_dev=s_used)   # [b,N] = s T_loc I_all^T  clip.py:141
         ctx.save_for_backward(image_features, text_features, i_n, t_n, i_all, t_all, li, lt, s_raw, s_used)
-        ctx.gather, ctx.rank, ctx.world = gather, rank, world
+        ctx.gather, ctx.rank, ctx.world, ctx.n = gather, rank, world, n
+        if n_pad != n:
+            return li[:, :n], lt[:, :n]
         return li, lt
 
     @staticmethod
     def backward(ctx, dli, dlt):
         image_features, text_features, i_n, t_n, i_all, t_all, li, lt, s_raw, s_used = ctx.saved_tensors
-        b, e = i_n.shape
-        dli = dli.contiguous().float()
-        dlt = dlt.contiguous().float()
+        b, e = image_features.shape
+        n, n_pad = ctx.n, li.shape[1]
+        if n_pad != n:      # odd batch: zero-padded columns (rare path, plain copies)
+            pad = torch.zeros(2, b, n_pad, device=li.device, dtype=torch.float32)
+            pad[0, :, :n] = dli
+            pad[1, :, :n] = dlt
+            dli, dlt = pad[0], pad[1]
+        else:
+            dli = dli.contiguous().float()
+            dlt = dlt.contiguous().float()
         dli16, dlt16 = cast_bf16(dli), cast_bf16(dlt)
+        i_loc, t_loc = i_n[:b], t_n[:b]
         # local-side terms: dI_n = s * dli T_all ; dT_n = s * dlt I_all          (B read MN-major)
         di_n = ops.gemm(dli16, t_all, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
         dt_n = ops.gemm(dlt16, i_all, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
         # gathered-side terms: dT_all = s * dli^T I_loc ; dI_all = s * dlt^T T_loc   (A, B read MN-major)
-        dt_all = ops.gemm(dli16, i_n, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
-        di_all = ops.gemm(dlt16, t_n, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
+        dt_all = ops.gemm(dli16, i_loc, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
+        di_all = ops.gemm(dlt16, t_loc, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s_used)
         if ctx.gather:
             both = torch.cat([di_all, dt_all], dim=1)
             mine = torch.empty(b, 2 * e, device=both.device, dtype=torch.float32)
@@ -107,8 +127,8 @@ class ClipLogits(torch.autograd.Function):
             di_n = di_n + mine[:, :e]
             dt_n = dt_n + mine[:, e:]
         else:
-            di_n = di_n + di_all
-            dt_n = dt_n + dt_all
+            di_n = di_n + di_all[:b]
+            dt_n = dt_n + dt_all[:b]
         d_img = l2norm_bwd(di_n.contiguous(), image_features, 0.0)
         d_txt = l2norm_bwd(dt_n.contiguous(), text_features, 1e-10)
         # d logit_scale = exp(ls) * sum(dlogits * logits) / s_used
@@ -125,8 +145,10 @@ class ClipInfoCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, li, lt, label0, stats):
         lib = ops.lib_for(li)
-        li = li.contiguous()
-        lt = lt.contiguous()
+        if li.stride(1) != 1:
+            li = li.contiguous()
+        if lt.stride(1) != 1:
+            lt = lt.contiguous()
         b, n = li.shape
         acc = torch.zeros(2, device=li.device, dtype=torch.float32)
         cnt = torch.zeros(2, device=li.device, dtype=torch.int32)
@@ -149,8 +171,8 @@ class ClipInfoCE(torch.autograd.Function):
         lib = ops.lib_for(li)
         b, n = li.shape
         g = g.contiguous().float()
-        dli = torch.empty_like(li)
-        dlt = torch.empty_like(lt)
+        dli = torch.empty(b, n, device=li.device, dtype=torch.float32)
+        dlt = torch.empty(b, n, device=li.device, dtype=torch.float32)
         for z, lse, d in ((li, lse_i, dli), (lt, lse_t, dlt)):
             _lib.check(lib.dc_ce_strip_bwd(_PTR(z.data_ptr()), z.stride(0), b, n, ctx.label0, _PTR(lse.data_ptr()),
                                            _PTR(g.data_ptr()), 1.0 / (2.0 * b), _PTR(d.data_ptr()), d.stride(0), 1,
