@@ -30,6 +30,14 @@ TRAIN_GFLOP_PER_PAIR = 43.9   # fwd 14.78 + 2x bwd, frozen con
 CPU_SAMPLE_BATCH = 32         # BASELINE configs[0]
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        print("[bench %.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,8 +60,13 @@ def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     sd = synth.clip_vit_state_dict(seed=0)
     images = synth.synth_images(batch, seed=0)
     ids = synth.synth_token_ids(batch, seed=0)
+    log("cpu arm: %d threads, warm-up" % cores)
     for _ in range(warmup):
+        tw = time.perf_counter()
         clip_ref.clip_step(sd, images, ids)
+        tw = time.perf_counter() - tw
+    steps = max(1, min(steps, int(25.0 / max(tw, 1e-3))))     # bound the sample to ~25 s of CPU work
+    log("cpu arm: warm step %.2fs -> timing %d steps" % (tw, steps))
     t0 = time.perf_counter()
     for _ in range(steps):
         clip_ref.clip_step(sd, images, ids)
@@ -67,9 +80,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
+    steps = max(1, min(args.steps, 8))
     warm = max(1, min(args.warmup, 2))
     cb = cpu_reference_steps(steps, warm)
+    steps = int(cb["sample"].split()[0])
     line = {
         "impl": "reference", "metric": "image-text pairs/sec", "value": cb["value"], "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
@@ -240,8 +254,11 @@ def run_native(args):
             done[s].record(main)
             loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
+    log("model + inputs ready; warm-up")
     for _ in range(max(args.warmup, 3)):
         step(dev_imgs[0], dev_ids[0])
+    torch.cuda.synchronize()
+    log("warm-up done; timing %d resident steps" % args.steps)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -249,9 +266,12 @@ def run_native(args):
     ms = timed(loop_resident, args.steps)
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
+    log("resident: %.2f ms/step" % (ms / args.steps))
     e2e = None
     if not args.no_e2e:
         loop_e2e(2)   # warm the copy path
+        torch.cuda.synchronize()
+        log("timing e2e")
         ms_e2e = timed(loop_e2e, args.steps)
         e2e = {"value": world * b * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
                "h2d_bytes_per_step": host_imgs[0].numel() * 4 + host_ids[0].numel() * 8, "d2h_bytes_per_step": 4,
@@ -293,10 +313,18 @@ def run_native(args):
                              "frac_of_sustained": (b * args.steps / (ms / 1e3) * TRAIN_GFLOP_PER_PAIR / 1e3) /
                              peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None}}
 
+    log("roofline probe done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_steps(4, 1)
-        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # separate process: its thread pool / a slow host cannot stall or perturb the GPU arm
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
+                                "--warmup", "1"], capture_output=True, text=True, timeout=240)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:   # reported, never silently dropped
+            cpu = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "cpu baseline leg failed: %r" % (ex,)}
+        log("cpu baseline done")
 
     if rank == 0:
         line = {
