@@ -51,11 +51,33 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def pick_cpu_threads():
+    """The reference's CPU path is PyTorch eager; more threads is not monotonically faster on these GEMM sizes
+    (128 threads measured 40x SLOWER than 8 on the GPU box).  Time the path's dominant op (the c_fc Linear of a
+    bs-32 ViT step, [1600x768]x[768x3072]) at a few thread counts and use the fastest — the best the host can do."""
+    import torch
+    total = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, total) if c <= total})
+    a, w = torch.randn(1600, 768), torch.randn(3072, 768)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(a, w)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            torch.nn.functional.linear(a, w)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    log("cpu arm: picked %d of %d host threads" % (best, total))
+    return best
+
+
 def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
     """Times the oracle port of the reference step (fwd + ClipInfoCELoss + bwd, fp32) on the host cores."""
     import torch
     from oracle import clip_ref, synth
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads()
     torch.set_num_threads(cores)
     sd = synth.clip_vit_state_dict(seed=0)
     images = synth.synth_images(batch, seed=0)

@@ -3,11 +3,12 @@
 //   out[M,N] (op)= epilogue(alpha * sum_k A(m,k) * B(n,k)),  bf16 operands, fp32 accumulate in TMEM.
 //
 // One CTA per SM (persistent, static tile schedule, n-fastest so concurrently running CTAs share
-// the same A rows / the whole of B through L2).  256 threads:
+// the same A rows / the whole of B through L2).  384 threads:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor 2-D boxes -> 128B-swizzled smem stages)
 //   warp 1   : UMMA issuer   (one elected lane, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
 //   warp 2   : TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4-7: epilogue      (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global)
+//   warps 4-11: epilogue     (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global; two warps per
+//                             TMEM lane quadrant, each draining half of the tile's columns)
 // Three pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue; the epilogue of
 // tile i overlaps the main loop of tile i+1), and the tile loop itself.
 //
@@ -40,7 +41,8 @@ struct GemmKParams {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -49,79 +51,140 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;  // per-epilogue-warp bias slice
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
 };
 
-// 8 consecutive output columns of one row.
-__device__ __forceinline__ void epilogue8(const GemmKParams& p, float alpha, int row, int col,
-                                          const uint32_t* acc /*8 fp32 bits*/) {
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[i]) * alpha;
-  if (p.bias != nullptr && p.epi != DC_EPI_F32_ATOMIC && p.epi != DC_EPI_BF16_DGELU) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-  }
+// ---------------------------------------------------------------------------------------------- epilogue
+// One epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) x BN/2 columns of a tile.  Everything
+// the math needs from global memory is fetched BEFORE it is needed: the bias slice is loaded to registers
+// before the warp blocks on the accumulator barrier and parked in per-warp shared memory; the aux operand
+// (residual / pre-activation) of chunk c+1 is in flight while chunk c is processed.  The epilogue mode is a
+// compile-time parameter (one branch per tile), so there is no indirect branch in the inner loop.
+template <int EPI>
+__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, int row, int col, float (&v)[8], const uint4& ax) {
   const size_t o = static_cast<size_t>(row) * p.ldo + col;
-  switch (p.epi) {
-    case DC_EPI_BF16: {
-      uint4 w;
-      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-    } break;
-    case DC_EPI_BF16_GELU: {
-      uint4 u, h;
-      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out2) + static_cast<size_t>(row) * p.ldo2 + col) = u;
+  if (EPI == DC_EPI_BF16) {
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+  } else if (EPI == DC_EPI_BF16_GELU) {
+    uint4 u, h;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out2) + static_cast<size_t>(row) * p.ldo2 + col) = u;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-      h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
-      h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = h;
-    } break;
-    case DC_EPI_BF16_RESID: {
-      const uint4 r = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
-      float2 f;
-      f = unpack_bf16x2(r.x); v[0] += f.x; v[1] += f.y;
-      f = unpack_bf16x2(r.y); v[2] += f.x; v[3] += f.y;
-      f = unpack_bf16x2(r.z); v[4] += f.x; v[5] += f.y;
-      f = unpack_bf16x2(r.w); v[6] += f.x; v[7] += f.y;
-      uint4 w;
-      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-    } break;
-    case DC_EPI_BF16_DGELU: {
-      const uint4 r = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
-      float2 f;
-      f = unpack_bf16x2(r.x); v[0] *= quick_gelu_grad(f.x); v[1] *= quick_gelu_grad(f.y);
-      f = unpack_bf16x2(r.y); v[2] *= quick_gelu_grad(f.x); v[3] *= quick_gelu_grad(f.y);
-      f = unpack_bf16x2(r.z); v[4] *= quick_gelu_grad(f.x); v[5] *= quick_gelu_grad(f.y);
-      f = unpack_bf16x2(r.w); v[6] *= quick_gelu_grad(f.x); v[7] *= quick_gelu_grad(f.y);
-      uint4 w;
-      w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-      w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-    } break;
-    case DC_EPI_F32: {
-      float* dst = static_cast<float*>(p.out) + o;
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } break;
-    case DC_EPI_F32_ATOMIC: {
-      float* dst = static_cast<float*>(p.out) + o;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                   "f"(v[3])
-                   : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                   "f"(v[7])
-                   : "memory");
-    } break;
-    default: break;
+    for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
+    h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
+    h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = h;
+  } else if (EPI == DC_EPI_BF16_RESID) {
+    float2 f;
+    f = unpack_bf16x2(ax.x); v[0] += f.x; v[1] += f.y;
+    f = unpack_bf16x2(ax.y); v[2] += f.x; v[3] += f.y;
+    f = unpack_bf16x2(ax.z); v[4] += f.x; v[5] += f.y;
+    f = unpack_bf16x2(ax.w); v[6] += f.x; v[7] += f.y;
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+  } else if (EPI == DC_EPI_BF16_DGELU) {
+    float2 f;
+    f = unpack_bf16x2(ax.x); v[0] *= quick_gelu_grad(f.x); v[1] *= quick_gelu_grad(f.y);
+    f = unpack_bf16x2(ax.y); v[2] *= quick_gelu_grad(f.x); v[3] *= quick_gelu_grad(f.y);
+    f = unpack_bf16x2(ax.z); v[4] *= quick_gelu_grad(f.x); v[5] *= quick_gelu_grad(f.y);
+    f = unpack_bf16x2(ax.w); v[6] *= quick_gelu_grad(f.x); v[7] *= quick_gelu_grad(f.y);
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
+  } else if (EPI == DC_EPI_F32) {
+    float* dst = static_cast<float*>(p.out) + o;
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {  // DC_EPI_F32_ATOMIC
+    float* dst = static_cast<float*>(p.out) + o;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
+                 "f"(v[7])
+                 : "memory");
+  }
+}
+
+// Waits for the accumulator, then drains this warp's 32 rows x (NCH * 32) columns starting at column `colbase`.
+template <int EPI, int NCH>
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, float alpha, uint32_t taddr, int row, int colbase,
+                                              float* s_bias, uint64_t* tfull, uint32_t parity) {
+  constexpr bool HAS_AUX = (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU);
+  constexpr bool HAS_BIAS = (EPI != DC_EPI_F32_ATOMIC && EPI != DC_EPI_BF16_DGELU);
+  const int lane = lane_id();
+  const bool row_ok = row < p.M;
+  const bool use_bias = HAS_BIAS && p.bias != nullptr;
+  // (1) bias slice -> registers (parked in smem after the barrier wait)
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (use_bias && lane < NCH * 8) {
+    const int c = colbase + lane * 4;
+    if (c < p.N) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  }
+  // (2) aux of chunk 0 in flight
+  uint4 ax[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) ax[g] = make_uint4(0u, 0u, 0u, 0u);
+  if (HAS_AUX && row_ok) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = colbase + g * 8;
+      if (col < p.N) ax[g] = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
+    }
+  }
+  mbar_wait(tfull, parity);
+  tc_fence_after();
+  if (HAS_BIAS) {
+    __syncwarp();
+    if (lane < NCH * 8) *reinterpret_cast<float4*>(s_bias + lane * 4) = bv;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col0 = colbase + c * 32;
+    uint4 axn[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) axn[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_AUX && row_ok && c + 1 < NCH) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + 32 + g * 8;
+        if (col < p.N) axn[g] = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
+      }
+    }
+    if (col0 < p.N) {  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(taddr + static_cast<uint32_t>(c * 32), r);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int col = col0 + g * 8;
+          if (col < p.N) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * alpha;
+            if (use_bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 8 + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            epilogue_store8<EPI>(p, row, col, v, ax[g]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ax[g] = axn[g];
   }
 }
 
@@ -139,6 +202,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -245,7 +309,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM -> regs -> global)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;     // which half of the tile's columns
+    constexpr int NCH = BN / 64;          // 32-column chunks per warp
+    float* s_bias = s_bias_all + (warp - 4) * (BN / 2);
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
     uint32_t aphase = 0;
@@ -254,25 +321,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int mn = t - split * tiles_mn;
       const int m_blk = mn / p.num_n;
       const int n_blk = mn - m_blk * p.num_n;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + static_cast<uint32_t>(c * 32), r);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < p.N) epilogue8(p, alpha, row, col, &r[g * 8]);
-          }
-        }
+      const int colbase = n_blk * BN + half * (BN / 2);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + half * (BN / 2));
+      switch (p.epi) {
+        case DC_EPI_BF16: epilogue_tile<DC_EPI_BF16, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        case DC_EPI_BF16_GELU: epilogue_tile<DC_EPI_BF16_GELU, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        case DC_EPI_BF16_RESID: epilogue_tile<DC_EPI_BF16_RESID, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        case DC_EPI_BF16_DGELU: epilogue_tile<DC_EPI_BF16_DGELU, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        case DC_EPI_F32: epilogue_tile<DC_EPI_F32, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
       }
       tc_fence_before();
       __syncwarp();
@@ -318,16 +377,7 @@ int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
 
   int BN = a.block_n;
   const int sms = sm_count();
-  if (BN == 0) {
-    // Pick the tile width that minimises (waves x per-tile cost); 256 is ~15 % more efficient per flop.
-    const long long nm = (a.M + BM - 1) / BM;
-    auto cost = [&](int bn) {
-      long long tiles = nm * ((a.N + bn - 1) / bn);
-      long long waves = (tiles + sms - 1) / sms;
-      return static_cast<double>(waves) * bn * (bn == 256 ? 1.0 : 1.15);
-    };
-    BN = (a.N <= 128 || cost(128) < cost(256)) ? 128 : 256;
-  }
+  if (BN == 0) BN = (a.N <= 128) ? 128 : 256;   // 128x256 tiles feed the tensor pipe ~25 % better (measured)
   if (BN != 128 && BN != 256) return set_error("gemm: block_n must be 128 or 256");
 
   GemmKParams p;
