@@ -34,6 +34,7 @@ class GemmArgs(ctypes.Structure):
         ("bias", c_void_p),
         ("aux", c_void_p), ("ldaux", c_int),
         ("splits", c_int), ("block_n", c_int),
+        ("colsum", c_void_p),
         ("alpha_dev", c_void_p),
     ]
 
@@ -60,13 +61,13 @@ SIGNATURES = {
     "dc_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),
     "dc_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_colsum_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dc_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "dc_multi_cast_f32_bf16": (c_int, [c_void_p, c_int, c_ull, c_void_p]),
     "dc_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dc_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                                 c_void_p]),
+    "dc_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_void_p]),
     "dc_patchify": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dc_vit_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "dc_text_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -182,10 +182,13 @@ __global__ void __launch_bounds__(LP * 2) attn_fwd_kernel(const bf16* __restrict
 template <int LP>
 __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
                                                           const bf16* __restrict__ dout, const float* __restrict__ lse,
-                                                          bf16* __restrict__ dqkv, int L, int heads, int causal) {
+                                                          bf16* __restrict__ dqkv, float* __restrict__ dbias, int L,
+                                                          int heads, int causal) {
   constexpr int NT = LP / 8;
   constexpr int KT = LP / 16;
   constexpr int PS = LP + 8;  // row stride of the [LP][LP] P / dS tiles
+  __shared__ float s_colsum[3 * HD];  // per-CTA column sums of dQ | dK | dV -> in_proj_bias gradient
+  for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x) s_colsum[i] = 0.f;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sK = sQ + LP * HS;
@@ -283,67 +286,85 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
     }
   }
   __syncthreads();
-  if (m0 >= L) return;
-
-  bf16* dbase = dqkv + static_cast<size_t>(b) * L * ld + h * HD;
-  float acc[HD / 8][4];
-  auto zero_acc = [&]() {
+  if (m0 < L) {
+    bf16* dbase = dqkv + static_cast<size_t>(b) * L * ld + h * HD;
+    float acc[HD / 8][4];
+    auto zero_acc = [&]() {
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
-  };
-  auto store_acc = [&](bf16* dst) {
+      for (int n = 0; n < HD / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+    };
+    // rows >= L of every accumulator are exactly zero (P and dS are zero there), so no masking is needed
+    auto store_acc = [&](bf16* dst, int which) {
 #pragma unroll
-    for (int n = 0; n < HD / 8; ++n) {
-      const int c = n * 8 + 2 * t;
-      if (r0 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r0) * ld + c) = pack_bf16x2(acc[n][0], acc[n][1]);
-      if (r1 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r1) * ld + c) = pack_bf16x2(acc[n][2], acc[n][3]);
+      for (int n = 0; n < HD / 8; ++n) {
+        const int c = n * 8 + 2 * t;
+        if (r0 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r0) * ld + c) = pack_bf16x2(acc[n][0], acc[n][1]);
+        if (r1 < L) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(r1) * ld + c) = pack_bf16x2(acc[n][2], acc[n][3]);
+        if (dbias != nullptr) {
+          float s0 = acc[n][0] + acc[n][2], s1 = acc[n][1] + acc[n][3];
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          if (g == 0) {
+            atomicAdd(&s_colsum[which * HD + c], s0);
+            atomicAdd(&s_colsum[which * HD + c + 1], s1);
+          }
+        }
+      }
+    };
+    // dQ[q][d] = sum_key dS[q][key] K[key][d]
+    zero_acc();
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      uint32_t a[4];
+      load_a(sdS, PS, m0, k * 16, a);
+#pragma unroll
+      for (int n = 0; n < HD / 8; n += 2) {
+        uint32_t bb[4];
+        load_b_kn(sK, HS, n * 8, k * 16, bb);
+        mma_bf16(acc[n], a, bb[0], bb[1]);
+        mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+      }
     }
-  };
-  // dQ[q][d] = sum_key dS[q][key] K[key][d]
-  zero_acc();
+    store_acc(dbase, 0);
+    // dK[key][d] = sum_q dS[q][key] Q[q][d]   (this warp's rows are keys now)
+    zero_acc();
 #pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    uint32_t a[4];
-    load_a(sdS, PS, m0, k * 16, a);
+    for (int k = 0; k < KT; ++k) {
+      uint32_t a[4];
+      load_a_t(sdS, PS, m0, k * 16, a);
 #pragma unroll
-    for (int n = 0; n < HD / 8; n += 2) {
-      uint32_t bb[4];
-      load_b_kn(sK, HS, n * 8, k * 16, bb);
-      mma_bf16(acc[n], a, bb[0], bb[1]);
-      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+      for (int n = 0; n < HD / 8; n += 2) {
+        uint32_t bb[4];
+        load_b_kn(sQ, HS, n * 8, k * 16, bb);
+        mma_bf16(acc[n], a, bb[0], bb[1]);
+        mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+      }
     }
+    store_acc(dbase + D, 1);
+    // dV[key][d] = sum_q P[q][key] dO[q][d]
+    zero_acc();
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      uint32_t a[4];
+      load_a_t(sP, PS, m0, k * 16, a);
+#pragma unroll
+      for (int n = 0; n < HD / 8; n += 2) {
+        uint32_t bb[4];
+        load_b_kn(sdO, HS, n * 8, k * 16, bb);
+        mma_bf16(acc[n], a, bb[0], bb[1]);
+        mma_bf16(acc[n + 1], a, bb[2], bb[3]);
+      }
+    }
+    store_acc(dbase + 2 * D, 2);
   }
-  store_acc(dbase);
-  // dK[key][d] = sum_q dS[q][key] Q[q][d]   (this warp's rows are keys now)
-  zero_acc();
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    uint32_t a[4];
-    load_a_t(sdS, PS, m0, k * 16, a);
-#pragma unroll
-    for (int n = 0; n < HD / 8; n += 2) {
-      uint32_t bb[4];
-      load_b_kn(sQ, HS, n * 8, k * 16, bb);
-      mma_bf16(acc[n], a, bb[0], bb[1]);
-      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
-    }
+  if (dbias != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * HD; i += blockDim.x)
+      atomicAdd(&dbias[(i / HD) * D + h * HD + (i % HD)], s_colsum[i]);
   }
-  store_acc(dbase + D);
-  // dV[key][d] = sum_q P[q][key] dO[q][d]
-  zero_acc();
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    uint32_t a[4];
-    load_a_t(sP, PS, m0, k * 16, a);
-#pragma unroll
-    for (int n = 0; n < HD / 8; n += 2) {
-      uint32_t bb[4];
-      load_b_kn(sdO, HS, n * 8, k * 16, bb);
-      mma_bf16(acc[n], a, bb[0], bb[1]);
-      mma_bf16(acc[n + 1], a, bb[2], bb[3]);
-    }
-  }
-  store_acc(dbase + 2 * D);
 }
 
 template <int LP>
@@ -366,8 +387,8 @@ static int launch_fwd(const bf16* qkv, bf16* out, float* lse, int batch, int L, 
   return 0;
 }
 template <int LP>
-static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int batch, int L,
-                      int heads, int causal, cudaStream_t st) {
+static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, float* dbias,
+                      int batch, int L, int heads, int causal, cudaStream_t st) {
   auto kern = attn_bwd_kernel<LP>;
   const size_t smem = attn_bwd_smem<LP>();
   static bool set = false;
@@ -376,7 +397,7 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_bwd)", e);
     set = true;
   }
-  kern<<<batch * heads, LP * 2, smem, st>>>(qkv, out, dout, lse, dqkv, L, heads, causal);
+  kern<<<batch * heads, LP * 2, smem, st>>>(qkv, out, dout, lse, dqkv, dbias, L, heads, causal);
   DC_CHECK_LAUNCH("attention_bwd");
   return 0;
 }
@@ -397,16 +418,16 @@ int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, i
   return launch_fwd<80>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, L, heads, causal, st);
 }
 
-int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                     int L, int heads, int causal, dc_stream_t stream) {
+int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
+                     int batch, int L, int heads, int causal, dc_stream_t stream) {
   if (batch <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");
   if (L <= 64)
     return launch_bwd<64>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,
-                          static_cast<bf16*>(dqkv), batch, L, heads, causal, st);
+                          static_cast<bf16*>(dqkv), dbias, batch, L, heads, causal, st);
   return launch_bwd<80>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,
-                        static_cast<bf16*>(dqkv), batch, L, heads, causal, st);
+                        static_cast<bf16*>(dqkv), dbias, batch, L, heads, causal, st);
 }
 
 }  // extern "C"

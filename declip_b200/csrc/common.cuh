@@ -73,6 +73,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tm, uint
       : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group); OOB rows/cols of the box are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_2d(const void* tm, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -156,7 +166,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(b);
 }
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid via one MUFU op: 0.5 + 0.5 * tanh(x / 2)  (tanh.approx.f32, rel. error 2^-11 — below bf16 resolution)
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
 // QuickGELU (reference: prototype/model/image_encoder/base_transformer.py:24-26): x * sigmoid(1.702 x)
 __device__ __forceinline__ float quick_gelu(float x) { return x * sigmoidf_fast(1.702f * x); }
 __device__ __forceinline__ float quick_gelu_grad(float x) {

@@ -145,6 +145,7 @@ static dc_gemm_args gemm_args(const void* A, int lda, int a_mn, const void* B, i
   a.bias = nullptr; a.aux = nullptr; a.ldaux = 0;
   a.splits = 0; a.block_n = 0;
   a.alpha_dev = nullptr;
+  a.colsum = nullptr;
   return a;
 }
 
@@ -196,6 +197,11 @@ static int layers_forward(const dc_tower_cfg& c, TowerWs& w, const void* const* 
 }
 
 // dx_top: gradient w.r.t. xs[layers] (in w.dxa); on return the gradient w.r.t. xs[0] is in w.dxa.
+// Bias gradients are fused into the kernel that PRODUCES the corresponding dY (no separate column-sum passes):
+//   c_proj.bias  (colsum of d xs[l+1]) : LN1-backward of layer l+1 (`dcol`), or `top_colsum` rows for the last layer
+//   c_fc.bias    (colsum of dU)        : DGELU epilogue of the c_proj dgrad GEMM
+//   out_proj.bias(colsum of d xmid)    : LN2-backward of the same layer
+//   in_proj_bias (colsum of dqkv)      : attention backward kernel
 static int layers_backward(const dc_tower_cfg& c, TowerWs& w, const void* const* wb, const float* const* wf,
                            float* const* grads, cudaStream_t st) {
   const int M = c.batch * c.seq_len, D = c.width;
@@ -210,18 +216,24 @@ static int layers_backward(const dc_tower_cfg& c, TowerWs& w, const void* const*
     bf16* dx = w.dxa;    // grad wrt xs[l+1]
     bf16* dmid = w.dxb;  // grad wrt xmid
     // MLP branch
-    DC_TRY(linear_dgrad(dx, w_pr, M, D, 4 * D, DC_EPI_BF16_DGELU, w.du, L.u, st));   // dU = (dx Wproj) * gelu'(u)
-    DC_TRY(linear_wgrad(dx, L.h, M, D, 4 * D, g[8], g[9], st));
+    {
+      dc_gemm_args a = gemm_args(dx, D, 0, w_pr, 4 * D, 1, M, 4 * D, D, DC_EPI_BF16_DGELU, w.du, 4 * D);
+      a.aux = L.u; a.ldaux = 4 * D;
+      a.colsum = g[7];                                                                // d c_fc.bias
+      DC_TRY(gemm_bf16(a, st));                                                       // dU = (dx Wproj) * gelu'(u)
+    }
+    DC_TRY(linear_wgrad(dx, L.h, M, D, 4 * D, g[8], nullptr, st));
     DC_TRY(linear_dgrad(w.du, w_fc, M, 4 * D, D, DC_EPI_BF16, w.dtmp, nullptr, st));  // dLN2out
-    DC_TRY(linear_wgrad(w.du, L.ln2, M, 4 * D, D, g[6], g[7], st));
-    DC_TRY(dc_layernorm_bwd(w.dtmp, L.xmid, f[4], L.mean2, L.rstd2, dx, dmid, g[10], g[11], M, D, st));
+    DC_TRY(linear_wgrad(w.du, L.ln2, M, 4 * D, D, g[6], nullptr, st));
+    DC_TRY(dc_layernorm_bwd(w.dtmp, L.xmid, f[4], L.mean2, L.rstd2, dx, dmid, g[10], g[11], g[3], M, D, st));
     // attention branch
     DC_TRY(linear_dgrad(dmid, w_out, M, D, D, DC_EPI_BF16, w.dtmp, nullptr, st));     // dAttnOut
-    DC_TRY(linear_wgrad(dmid, L.attn, M, D, D, g[2], g[3], st));
-    DC_TRY(dc_attention_bwd(L.qkv, L.attn, w.dtmp, L.lse, w.dqkv, c.batch, c.seq_len, c.heads, c.causal, st));
+    DC_TRY(linear_wgrad(dmid, L.attn, M, D, D, g[2], nullptr, st));
+    DC_TRY(dc_attention_bwd(L.qkv, L.attn, w.dtmp, L.lse, w.dqkv, g[1], c.batch, c.seq_len, c.heads, c.causal, st));
     DC_TRY(linear_dgrad(w.dqkv, w_in, M, 3 * D, D, DC_EPI_BF16, w.dtmp, nullptr, st));  // dLN1out
-    DC_TRY(linear_wgrad(w.dqkv, L.ln1, M, 3 * D, D, g[0], g[1], st));
-    DC_TRY(dc_layernorm_bwd(w.dtmp, w.xs[l], f[0], L.mean1, L.rstd1, dmid, dx, g[4], g[5], M, D, st));
+    DC_TRY(linear_wgrad(w.dqkv, L.ln1, M, 3 * D, D, g[0], nullptr, st));
+    float* dcol_prev = (l > 0) ? grads[12 * (l - 1) + 9] : nullptr;                     // c_proj.bias of layer l-1
+    DC_TRY(dc_layernorm_bwd(w.dtmp, w.xs[l], f[0], L.mean1, L.rstd1, dmid, dx, g[4], g[5], dcol_prev, M, D, st));
   }
   return 0;
 }
@@ -293,13 +305,14 @@ int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void*
     dc_gemm_args a = gemm_args(w.dfeat, E, 0, proj, E, 0, c.batch, D, E, DC_EPI_BF16, w.drow, D);
     DC_TRY(gemm_bf16(a, st));
   }
-  DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[4], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[4], xg[5], c.batch, D, st));
+  DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[4], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[4], xg[5],
+                          NL > 0 ? grads[12 * (NL - 1) + 9] : nullptr, c.batch, D, st));  // + c_proj.bias of the last layer
   cudaError_t e = cudaMemsetAsync(w.dxa, 0, static_cast<size_t>(M) * D * sizeof(bf16), st);
   if (e != cudaSuccess) return set_error_cuda("memset dx", e);
   DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));
   DC_TRY(layers_backward(c, w, w_bf16, w_f32, grads, st));
   // ln_pre backward, then positional / class embedding gradients
-  DC_TRY(dc_layernorm_bwd(w.dxa, w.tokens_pre, xf[2], w.mean_pre, w.rstd_pre, nullptr, w.dxb, xg[2], xg[3], M, D, st));
+  DC_TRY(dc_layernorm_bwd(w.dxa, w.tokens_pre, xf[2], w.mean_pre, w.rstd_pre, nullptr, w.dxb, xg[2], xg[3], nullptr, M, D, st));
   DC_TRY(dc_colsum_bf16(w.dxb, c.seq_len * D, xg[1], c.batch, c.seq_len * D, st));
   DC_TRY(dc_colsum_bf16(w.dxb, c.seq_len * D, xg[0], c.batch, D, st));
   return 0;
@@ -341,7 +354,8 @@ int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float*
   // text_projection: dW[E,D] += dfeat^T rows_ln ; db += colsum(dfeat) ; d rows_ln = dfeat W
   DC_TRY(linear_wgrad(w.dfeat, w.rows_ln, c.batch, E, D, xg[4], xg[5], st));
   DC_TRY(linear_dgrad(w.dfeat, wtp, c.batch, E, D, DC_EPI_BF16, w.drow, nullptr, st));
-  DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[2], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[2], xg[3], c.batch, D, st));
+  DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[2], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[2], xg[3],
+                          NL > 0 ? grads[12 * (NL - 1) + 9] : nullptr, c.batch, D, st));  // + c_proj.bias of the last layer
   cudaError_t e = cudaMemsetAsync(w.dxa, 0, static_cast<size_t>(M) * D * sizeof(bf16), st);
   if (e != cudaSuccess) return set_error_cuda("memset dx", e);
   DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));

@@ -19,6 +19,7 @@
 // Replaces (reference, /root/reference): every nn.Linear/F.linear/`@` on the training hot path —
 // prototype/model/image_encoder/base_transformer.py:33-41, visual_transformer.py:56,72,
 // text_encoder/text_transformer.py:203, model/clip.py:140-141 — and their autograd backward.
+#include <string.h>
 #include "common.cuh"
 #include "internal.h"
 
@@ -37,6 +38,7 @@ struct GemmKParams {
   const bf16* aux;
   int ldaux;
   const float* alpha_dev;
+  float* colsum;
 };
 
 constexpr int BM = 128;
@@ -51,76 +53,70 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STAGING_BYTES = EPI_WARPS * 2048;       // per-epilogue-warp 32x32 bf16 TMA-store staging
   static constexpr int BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;  // per-epilogue-warp bias slice
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES +
+                                    1024 /*align slack*/;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue
-// One epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) x BN/2 columns of a tile.  Everything
-// the math needs from global memory is fetched BEFORE it is needed: the bias slice is loaded to registers
-// before the warp blocks on the accumulator barrier and parked in per-warp shared memory; the aux operand
-// (residual / pre-activation) of chunk c+1 is in flight while chunk c is processed.  The epilogue mode is a
-// compile-time parameter (one branch per tile), so there is no indirect branch in the inner loop.
-template <int EPI>
-__device__ __forceinline__ void epilogue_store8(const GemmKParams& p, int row, int col, float (&v)[8], const uint4& ax) {
-  const size_t o = static_cast<size_t>(row) * p.ldo + col;
-  if (EPI == DC_EPI_BF16) {
-    uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-  } else if (EPI == DC_EPI_BF16_GELU) {
-    uint4 u, h;
-    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out2) + static_cast<size_t>(row) * p.ldo2 + col) = u;
+// One epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) x BN/2 columns of a tile, processed in
+// 32-column chunks.  Everything the math needs from global memory is fetched BEFORE it is needed: the bias slice
+// is loaded to registers before the warp blocks on the accumulator barrier and parked in per-warp shared memory;
+// the aux operand (residual / pre-activation) of chunk c+1 is in flight while chunk c is processed.
+// bf16 outputs leave through a per-warp 2 KiB staging buffer (64-byte swizzle, conflict-free st.shared.v4) and one
+// TMA store per 32x32 chunk: fully coalesced 64-byte row segments, OOB rows/cols clipped by the TMA unit, and the
+// LSU is free for the next chunk.  fp32 outputs (logit strips, features, split-K wgrad atomics) are written
+// directly.  The epilogue mode is a compile-time parameter (one branch per tile).
+__device__ __forceinline__ void stage_store_chunk(const float (&v)[32], uint8_t* stage, const CUtensorMap* tm, int col0,
+                                                  int row0) {
+  const int lane = lane_id();
+  if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
+  __syncwarp();
+  uint8_t* rowp = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;    // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = quick_gelu(v[i]);
-    h.x = pack_bf16x2(v[0], v[1]); h.y = pack_bf16x2(v[2], v[3]);
-    h.z = pack_bf16x2(v[4], v[5]); h.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = h;
-  } else if (EPI == DC_EPI_BF16_RESID) {
-    float2 f;
-    f = unpack_bf16x2(ax.x); v[0] += f.x; v[1] += f.y;
-    f = unpack_bf16x2(ax.y); v[2] += f.x; v[3] += f.y;
-    f = unpack_bf16x2(ax.z); v[4] += f.x; v[5] += f.y;
-    f = unpack_bf16x2(ax.w); v[6] += f.x; v[7] += f.y;
+  for (int j = 0; j < 4; ++j) {
     uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-  } else if (EPI == DC_EPI_BF16_DGELU) {
-    float2 f;
-    f = unpack_bf16x2(ax.x); v[0] *= quick_gelu_grad(f.x); v[1] *= quick_gelu_grad(f.y);
-    f = unpack_bf16x2(ax.y); v[2] *= quick_gelu_grad(f.x); v[3] *= quick_gelu_grad(f.y);
-    f = unpack_bf16x2(ax.z); v[4] *= quick_gelu_grad(f.x); v[5] *= quick_gelu_grad(f.y);
-    f = unpack_bf16x2(ax.w); v[6] *= quick_gelu_grad(f.x); v[7] *= quick_gelu_grad(f.y);
-    uint4 w;
-    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
-    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(static_cast<bf16*>(p.out) + o) = w;
-  } else if (EPI == DC_EPI_F32) {
-    float* dst = static_cast<float*>(p.out) + o;
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  } else {  // DC_EPI_F32_ATOMIC
-    float* dst = static_cast<float*>(p.out) + o;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                 "f"(v[3])
-                 : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]),
-                 "f"(v[7])
-                 : "memory");
+    w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+    w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = w;
   }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, stage, col0, row0);
+    bulk_commit();
+  }
+}
+
+// Column sums of a 32x32 chunk held one row per lane: butterfly reduce-scatter (31 shuffles); lane j ends with
+// the sum of column j.
+__device__ __forceinline__ float chunk_colsum(float (&v)[32]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
 }
 
 // Waits for the accumulator, then drains this warp's 32 rows x (NCH * 32) columns starting at column `colbase`.
 template <int EPI, int NCH>
-__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, float alpha, uint32_t taddr, int row, int colbase,
-                                              float* s_bias, uint64_t* tfull, uint32_t parity) {
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tm_out, const CUtensorMap* tm_out2,
+                                              float alpha, uint32_t taddr, int row0, int colbase, float* s_bias,
+                                              uint8_t* stage, uint64_t* tfull, uint32_t parity) {
   constexpr bool HAS_AUX = (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU);
   constexpr bool HAS_BIAS = (EPI != DC_EPI_F32_ATOMIC && EPI != DC_EPI_BF16_DGELU);
+  constexpr bool OUT_BF16 = (EPI <= DC_EPI_BF16_DGELU);
   const int lane = lane_id();
+  const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const bool use_bias = HAS_BIAS && p.bias != nullptr;
   // (1) bias slice -> registers (parked in smem after the barrier wait)
@@ -164,21 +160,64 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, float alpha,
       uint32_t r[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c * 32), r);
       tmem_ld_wait();
-      if (row_ok) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+      if (use_bias) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 4);
+          v[4 * g + 0] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+        }
+      }
+      if (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float a8[8];
+          float2 f;
+          f = unpack_bf16x2(ax[g].x); a8[0] = f.x; a8[1] = f.y;
+          f = unpack_bf16x2(ax[g].y); a8[2] = f.x; a8[3] = f.y;
+          f = unpack_bf16x2(ax[g].z); a8[4] = f.x; a8[5] = f.y;
+          f = unpack_bf16x2(ax[g].w); a8[6] = f.x; a8[7] = f.y;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (EPI == DC_EPI_BF16_RESID) v[8 * g + i] += a8[i];
+            else v[8 * g + i] *= quick_gelu_grad(a8[i]);
+          }
+        }
+      }
+      if (OUT_BF16) {
+        if (EPI == DC_EPI_BF16_GELU) {
+          stage_store_chunk(v, stage, tm_out2, col0, row0);   // pre-activation u (saved for backward)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+        }
+        stage_store_chunk(v, stage, tm_out, col0, row0);
+        if (p.colsum != nullptr) {                            // fused bias gradient: colsum += sum_rows out
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          const float cs = chunk_colsum(v);
+          if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
+        }
+      } else if (row_ok) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = col0 + g * 8;
           if (col < p.N) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * alpha;
-            if (use_bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 8 + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            float* dst = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col;
+            if (EPI == DC_EPI_F32) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
+            } else {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[8 * g]), "f"(v[8 * g + 1]),
+                           "f"(v[8 * g + 2]), "f"(v[8 * g + 3])
+                           : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(v[8 * g + 4]),
+                           "f"(v[8 * g + 5]), "f"(v[8 * g + 6]), "f"(v[8 * g + 7])
+                           : "memory");
             }
-            epilogue_store8<EPI>(p, row, col, v, ax[g]);
           }
         }
       }
@@ -191,18 +230,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, float alpha,
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
                  const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias_all = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+  float* s_bias_all = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,6 +251,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
+    if (p.epi <= DC_EPI_BF16_DGELU) prefetch_tensormap(&tmOut);
+    if (p.epi == DC_EPI_BF16_GELU) prefetch_tensormap(&tmOut2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -313,6 +356,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - 4) >> 2;     // which half of the tile's columns
     constexpr int NCH = BN / 64;          // 32-column chunks per warp
     float* s_bias = s_bias_all + (warp - 4) * (BN / 2);
+    uint8_t* stage = staging + (warp - 4) * 2048;
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
     uint32_t aphase = 0;
@@ -321,23 +365,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int mn = t - split * tiles_mn;
       const int m_blk = mn / p.num_n;
       const int n_blk = mn - m_blk * p.num_n;
-      const int row = m_blk * BM + quad * 32 + lane;
+      const int row0 = m_blk * BM + quad * 32;
       const int colbase = n_blk * BN + half * (BN / 2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(as * BN + half * (BN / 2));
+#define DC_EPI_CASE(E) \
+  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage, &tfull_bar[as], aphase); break
       switch (p.epi) {
-        case DC_EPI_BF16: epilogue_tile<DC_EPI_BF16, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
-        case DC_EPI_BF16_GELU: epilogue_tile<DC_EPI_BF16_GELU, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
-        case DC_EPI_BF16_RESID: epilogue_tile<DC_EPI_BF16_RESID, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
-        case DC_EPI_BF16_DGELU: epilogue_tile<DC_EPI_BF16_DGELU, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
-        case DC_EPI_F32: epilogue_tile<DC_EPI_F32, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
-        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, alpha, taddr, row, colbase, s_bias, &tfull_bar[as], aphase); break;
+        DC_EPI_CASE(DC_EPI_BF16);
+        DC_EPI_CASE(DC_EPI_BF16_GELU);
+        DC_EPI_CASE(DC_EPI_BF16_RESID);
+        DC_EPI_CASE(DC_EPI_BF16_DGELU);
+        DC_EPI_CASE(DC_EPI_F32);
+        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage,
+                                                       &tfull_bar[as], aphase); break;
       }
+#undef DC_EPI_CASE
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) bulk_wait_read0();  // staging smem must outlive the last TMA store's read
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -350,8 +400,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ------------------------------------------------------------------------------------ host side
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmO2,
+                       const GemmKParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -360,7 +410,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
@@ -419,8 +469,24 @@ int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   else               rc = make_tmap_2d(&tmB, a.B, a.N, a.K, a.ldb, 64, BK);
   if (rc) return rc;
 
+  // bf16 outputs leave through TMA stores of 32x32 boxes (64-byte swizzle)
+  CUtensorMap tmO, tmO2;
+  memset(&tmO, 0, sizeof(tmO));
+  memset(&tmO2, 0, sizeof(tmO2));
+  if (a.epilogue <= DC_EPI_BF16_DGELU) {
+    if (a.ldo & 7) return set_error("gemm: ldo must be a multiple of 8 for bf16 outputs");
+    rc = make_tmap_2d(&tmO, a.out, a.N, a.M, a.ldo, 32, 32, 64);
+    if (rc) return rc;
+    if (a.epilogue == DC_EPI_BF16_GELU) {
+      if (a.ldo2 & 7) return set_error("gemm: ldo2 must be a multiple of 8");
+      rc = make_tmap_2d(&tmO2, a.out2, a.N, a.M, a.ldo2, 32, 32, 64);
+      if (rc) return rc;
+    }
+  }
+  p.colsum = (a.epilogue <= DC_EPI_BF16_DGELU) ? a.colsum : nullptr;
+
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-#define DC_LAUNCH(BN_, AM_, BM_) return launch_gemm<BN_, AM_, BM_>(tmA, tmB, p, grid, stream)
+#define DC_LAUNCH(BN_, AM_, BM_) return launch_gemm<BN_, AM_, BM_>(tmA, tmB, tmO, tmO2, p, grid, stream)
   if (BN == 256) {
     if (!a.a_mn_major && !a.b_mn_major) DC_LAUNCH(256, false, false);
     if (!a.a_mn_major && a.b_mn_major) DC_LAUNCH(256, false, true);

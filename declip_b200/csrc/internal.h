@@ -16,7 +16,7 @@ int sm_count();
 // `ld` = row stride (elements); box = {box_inner (must be 64 -> 128 B), box_outer <= 256}.
 // OOB elements are zero-filled by the TMA unit, so ragged M/N/K tails need no special casing.
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
-                 int box_outer);
+                 int box_outer, int swizzle_bytes = 128);
 
 // launchers implemented in the .cu files, used by the composite encoders
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream);

@@ -73,22 +73,47 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const bf16* __restrict__ x,
 }
 
 // LayerNorm backward: dx = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;
-// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (register accumulation per lane across the
-// warp's rows, then shared-memory + global fp32 atomics once per block).
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy, and optionally dcol += sum_rows dx (the bias gradient of
+// the Linear that produced this LayerNorm's input — saves a separate column-sum pass over dx).
+// One warp per row, register accumulation per lane across the warp's rows, software-pipelined loads (the next
+// row's x/dy/dres are in flight while the current row is reduced), then smem + global fp32 atomics per block.
+template <int NV>
+struct LnRow {
+  uint4 x[NV], dy[NV], dr[NV];
+};
+template <int NV>
+__device__ __forceinline__ void ln_bwd_load(LnRow<NV>& r, const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                            const bf16* __restrict__ dres, size_t base, int lane) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 8;
+    r.x[j] = *reinterpret_cast<const uint4*>(x + base + c);
+    r.dy[j] = *reinterpret_cast<const uint4*>(dy + base + c);
+    if (dres != nullptr) r.dr[j] = *reinterpret_cast<const uint4*>(dres + base + c);
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const bf16* __restrict__ dres,
                                                      bf16* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int rows) {
+                                                     float* __restrict__ dbeta, float* __restrict__ dcol, int rows) {
   constexpr int W = NV * 256;
-  __shared__ float s_acc[2 * W];
-  for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) s_acc[i] = 0.f;
+  __shared__ float s_acc[3 * W];
+  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float g[NV][8], ag[NV][8], ab[NV][8];
+  float g[NV][8], ag[NV][8], ab[NV][8], ao[NV][8];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c = (lane + 32 * j) * 8;
@@ -97,35 +122,29 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     g[j][0] = g0.x; g[j][1] = g0.y; g[j][2] = g0.z; g[j][3] = g0.w;
     g[j][4] = g1.x; g[j][5] = g1.y; g[j][6] = g1.z; g[j][7] = g1.w;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { ag[j][i] = 0.f; ab[j][i] = 0.f; ao[j][i] = 0.f; }
   }
-  for (int row = warp; row < rows; row += nwarps) {
+  LnRow<NV> cur, nxt;
+  int row = warp;
+  if (row < rows) ln_bwd_load<NV>(cur, x, dy, dres, static_cast<size_t>(row) * W, lane);
+  for (; row < rows; row += nwarps) {
+    const int nrow = row + nwarps;
+    if (nrow < rows) ln_bwd_load<NV>(nxt, x, dy, dres, static_cast<size_t>(nrow) * W, lane);
     const size_t base = static_cast<size_t>(row) * W;
     const float mu = mean[row], rs = rstd[row];
-    float xh[NV][8], gy[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int c = (lane + 32 * j) * 8;
-      const uint4 ux = *reinterpret_cast<const uint4*>(x + base + c);
-      const uint4 ud = *reinterpret_cast<const uint4*>(dy + base + c);
       float xv[8], dv[8];
-      float2 f;
-      f = unpack_bf16x2(ux.x); xv[0] = f.x; xv[1] = f.y;
-      f = unpack_bf16x2(ux.y); xv[2] = f.x; xv[3] = f.y;
-      f = unpack_bf16x2(ux.z); xv[4] = f.x; xv[5] = f.y;
-      f = unpack_bf16x2(ux.w); xv[6] = f.x; xv[7] = f.y;
-      f = unpack_bf16x2(ud.x); dv[0] = f.x; dv[1] = f.y;
-      f = unpack_bf16x2(ud.y); dv[2] = f.x; dv[3] = f.y;
-      f = unpack_bf16x2(ud.z); dv[4] = f.x; dv[5] = f.y;
-      f = unpack_bf16x2(ud.w); dv[6] = f.x; dv[7] = f.y;
+      unpack8(cur.x[j], xv);
+      unpack8(cur.dy[j], dv);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        xh[j][i] = (xv[i] - mu) * rs;
-        gy[j][i] = dv[i] * g[j][i];
-        s1 += gy[j][i];
-        s2 += gy[j][i] * xh[j][i];
-        ag[j][i] += dv[i] * xh[j][i];
+        const float xh = (xv[i] - mu) * rs;
+        const float gy = dv[i] * g[j][i];
+        s1 += gy;
+        s2 += gy * xh;
+        ag[j][i] += dv[i] * xh;
         ab[j][i] += dv[i];
       }
     }
@@ -134,22 +153,30 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = (lane + 32 * j) * 8;
-      float o[8];
+      float xv[8], dv[8], o[8];
+      unpack8(cur.x[j], xv);
+      unpack8(cur.dy[j], dv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rs * (gy[j][i] - c1 - xh[j][i] * c2);
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (xv[i] - mu) * rs;
+        o[i] = rs * (dv[i] * g[j][i] - c1 - xh * c2);
+      }
       if (dres != nullptr) {
-        const uint4 ur = *reinterpret_cast<const uint4*>(dres + base + c);
-        float2 f;
-        f = unpack_bf16x2(ur.x); o[0] += f.x; o[1] += f.y;
-        f = unpack_bf16x2(ur.y); o[2] += f.x; o[3] += f.y;
-        f = unpack_bf16x2(ur.z); o[4] += f.x; o[5] += f.y;
-        f = unpack_bf16x2(ur.w); o[6] += f.x; o[7] += f.y;
+        float rv[8];
+        unpack8(cur.dr[j], rv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += rv[i];
+      }
+      if (dcol != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ao[j][i] += o[i];
       }
       uint4 w;
       w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
       w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
       *reinterpret_cast<uint4*>(dx + base + c) = w;
     }
+    cur = nxt;
   }
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -158,12 +185,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
     for (int i = 0; i < 8; ++i) {
       atomicAdd(&s_acc[c + i], ag[j][i]);
       atomicAdd(&s_acc[W + c + i], ab[j][i]);
+      if (dcol != nullptr) atomicAdd(&s_acc[2 * W + c + i], ao[j][i]);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < W; i += blockDim.x) {
     atomicAdd(&dgamma[i], s_acc[i]);
     atomicAdd(&dbeta[i], s_acc[W + i]);
+    if (dcol != nullptr) atomicAdd(&dcol[i], s_acc[2 * W + i]);
   }
 }
 
@@ -561,7 +590,7 @@ int dc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
 }
 
 int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int width,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, float* dcol, int rows, int width,
                      dc_stream_t stream) {
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -571,10 +600,10 @@ int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
   const bf16* rp = static_cast<const bf16*>(dres);
   bf16* dxp = static_cast<bf16*>(dx);
   switch (width) {
-    case 256: ln_bwd_kernel<1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
-    case 512: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
-    case 768: ln_bwd_kernel<3><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
-    case 1024: ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, rows); break;
+    case 256: ln_bwd_kernel<1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+    case 512: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+    case 768: ln_bwd_kernel<3><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+    case 1024: ln_bwd_kernel<4><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
     default: return set_error("layernorm: width must be 256, 512, 768 or 1024");
   }
   DC_CHECK_LAUNCH("layernorm_bwd");

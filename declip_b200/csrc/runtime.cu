@@ -31,7 +31,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
-                 int box_outer) {
+                 int box_outer, int swizzle_bytes) {
   if (g_encode == nullptr) return set_error("dc_init() was not called (no cuTensorMapEncodeTiled entry point)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error("tensor map: base pointer must be 16-byte aligned");
   if ((ld * 2) % 16 != 0) return set_error("tensor map: row stride must be a multiple of 16 bytes");
@@ -40,7 +40,9 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long ou
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err),

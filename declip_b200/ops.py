@@ -29,7 +29,7 @@ def lib_for(t):
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1.0, bias=None, aux=None, out=None,
-         out2=None, splits=0, block_n=0, alpha_dev=None):
+         out2=None, splits=0, block_n=0, alpha_dev=None, colsum=None):
     """out[M,N] (op)= epilogue(alpha * sum_k A(m,k) B(n,k)).
 
     a: [M,K] (or [K,M] if a_mn_major), b: [N,K] (or [K,N] if b_mn_major); both bf16, last dim contiguous.
@@ -69,6 +69,9 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1
         assert aux.dtype == torch.bfloat16 and aux.stride(-1) == 1
         args.aux, args.ldaux = aux.data_ptr(), aux.stride(0)
     args.splits, args.block_n = splits, block_n
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == N
+        args.colsum = colsum.data_ptr()
     if alpha_dev is not None:
         assert alpha_dev.dtype == torch.float32 and alpha_dev.is_cuda
         args.alpha_dev = alpha_dev.data_ptr()
@@ -90,14 +93,17 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, with_colsum=False):
     lib = lib_for(x)
     rows, width = x.shape
     dx = torch.empty_like(x)
     dgamma = torch.zeros(width, device=x.device, dtype=torch.float32)
     dbeta = torch.zeros(width, device=x.device, dtype=torch.float32)
+    dcol = torch.zeros(width, device=x.device, dtype=torch.float32) if with_colsum else None
     _lib.check(lib.dc_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx),
-                                    _ptr(dgamma), _ptr(dbeta), rows, width, _stream()), "dc_layernorm_bwd")
+                                    _ptr(dgamma), _ptr(dbeta), _ptr(dcol), rows, width, _stream()), "dc_layernorm_bwd")
+    if with_colsum:
+        return dx, dgamma, dbeta, dcol
     return dx, dgamma, dbeta
 
 
@@ -120,11 +126,11 @@ def attention_fwd(qkv, batch, L, heads, causal):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, batch, L, heads, causal):
+def attention_bwd(qkv, out, dout, lse, batch, L, heads, causal, dbias=None):
     lib = lib_for(qkv)
     dqkv = torch.empty_like(qkv)
-    _lib.check(lib.dc_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), batch, L, heads,
-                                    int(causal), _stream()), "dc_attention_bwd")
+    _lib.check(lib.dc_attention_bwd(_ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(dbias), batch, L,
+                                    heads, int(causal), _stream()), "dc_attention_bwd")
     return dqkv
 
 

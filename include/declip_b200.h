@@ -65,6 +65,8 @@ typedef struct {
   const void* aux; int ldaux; /* bf16 [M,N] or NULL */
   int splits;                 /* split-K factor, 0 = auto (only DC_EPI_F32_ATOMIC may split) */
   int block_n;                /* 0 = auto, else 128 or 256 */
+  float* colsum;              /* optional fp32 [N]: += sum over rows of the bf16-epilogue output (before rounding);
+                                 the bias gradient when `out` is a dY — fused, no extra pass over dY */
   const float* alpha_dev;     /* optional DEVICE scalar multiplied into alpha (e.g. the clamped exp(logit_scale),
                                  clip.py:133-134) so no host sync is needed; NULL = 1 */
 } dc_gemm_args;
@@ -76,9 +78,11 @@ int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
  * for backward.  width % 256 == 0, width <= 1024. */
 int dc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      int rows, int width, float eps, dc_stream_t stream);
-/* dx(bf16) = [dres +] LN'(dy); dgamma,dbeta (fp32 [width]) are ACCUMULATED (+=). dres may be NULL. */
+/* dx(bf16) = [dres +] LN'(dy); dgamma,dbeta (fp32 [width]) are ACCUMULATED (+=). dres may be NULL.
+ * dcol (fp32 [width], may be NULL) += sum_rows dx: the bias gradient of the Linear feeding this LayerNorm's input
+ * (out_proj / c_proj), fused here so no separate column-sum pass over dx is needed. */
 int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                     const void* dres, void* dx, float* dgamma, float* dbeta, int rows, int width,
+                     const void* dres, void* dx, float* dgamma, float* dbeta, float* dcol, int rows, int width,
                      dc_stream_t stream);
 /* out[c] += sum_r x[r,c] (bf16 in, fp32 accumulate): bias gradients of every Linear. */
 int dc_colsum_bf16(const void* x, int ldx, float* out, int rows, int cols, dc_stream_t stream);
@@ -96,8 +100,9 @@ int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsign
  * lse fp32 [batch*heads*L] saved for backward. */
 int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal,
                      dc_stream_t stream);
-int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int batch,
-                     int L, int heads, int causal, dc_stream_t stream);
+/* dbias (fp32 [3*width], may be NULL) += column sums of dqkv: the in_proj_bias gradient, fused. */
+int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
+                     int batch, int L, int heads, int causal, dc_stream_t stream);
 
 /* ------------------------------------------------------------------ embeddings
  * ViT: conv1 with kernel == stride == patch is a GEMM over non-overlapping patches

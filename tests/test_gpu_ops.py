@@ -50,6 +50,14 @@ def test_gemm_epilogues(cuda_dev):
     x = aux.float()
     s = torch.sigmoid(1.702 * x)
     assert _rel(ops.gemm(a, b, aux=aux, epilogue=ops.EPI_BF16_DGELU), want * (s * (1 + 1.702 * x * (1 - s)))) < 5e-3
+    cs = torch.ones(N, device=cuda_dev)
+    o = ops.gemm(a, b, aux=aux, epilogue=ops.EPI_BF16_DGELU, colsum=cs)     # fused bias gradient of the output
+    assert _rel(cs - 1, (want * (s * (1 + 1.702 * x * (1 - s)))).sum(0)) < 2e-3
+    # ragged N / M through the TMA-store epilogue (clipping) and a strided output view
+    big = torch.zeros(1000, 1024, device=cuda_dev, dtype=torch.bfloat16)
+    ops.gemm(a, b[:520], bias=bias[:520].contiguous(), out=big[:, 8:528])
+    assert _rel(big[:, 8:528], want[:, :520] + bias[:520]) < 4e-3
+    assert big[:, :8].abs().max().item() == 0 and big[:, 528:].abs().max().item() == 0
     sc = torch.tensor([2.5], device=cuda_dev)
     assert _rel(ops.gemm(a, b, epilogue=ops.EPI_F32, alpha_dev=sc), 2.5 * want) < 1e-5
     acc = torch.ones(N, K, device=cuda_dev)
@@ -81,8 +89,9 @@ def test_layernorm(cuda_dev, width, rows):
     dx, dg, db = ops.layernorm_bwd(dy, x, g, mean, rstd, dres)
     assert _rel(dx, xr.grad + dres.float()) < 5e-3
     assert _rel(dg, gr.grad) < 1e-3 and _rel(db, br.grad) < 1e-3
-    dx2, _, _ = ops.layernorm_bwd(dy, x, g, mean, rstd, None)
+    dx2, _, _, dcol = ops.layernorm_bwd(dy, x, g, mean, rstd, None, with_colsum=True)
     assert _rel(dx2, xr.grad) < 5e-3
+    assert _rel(dcol, xr.grad.sum(0)) < 2e-3 or (dcol - xr.grad.sum(0)).abs().max() < 2e-2   # fused bias gradient
 
 
 def test_colsum(cuda_dev):
@@ -121,8 +130,10 @@ def test_attention(cuda_dev, L, H, causal):
     assert torch.allclose(lse.view(B, H, L), lse_ref, atol=2e-3)
     dout = torch.randn(B * L, D, device=cuda_dev).bfloat16()
     o_ref.backward(dout.float())
-    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, causal)
+    dbias = torch.ones(3 * D, device=cuda_dev)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, causal, dbias=dbias)
     assert _rel(dqkv, qr.grad) < 2e-2 and _cos(dqkv, qr.grad) > 0.9995
+    assert _rel(dbias - 1, qr.grad.sum(0)) < 2e-2                      # fused in_proj_bias gradient
 
 
 def test_embeddings(cuda_dev):
