@@ -75,12 +75,21 @@ SIGNATURES = {
     "dc_gather_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_scatter_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_eot_index": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "dc_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "dc_l2norm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "dc_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
-    "dc_ce_strip_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+    "dc_ce_strip_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
-    "dc_ce_strip_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
-                                c_int, c_void_p]),
+    "dc_ce_strip_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                c_int, c_int, c_void_p]),
+    "dc_batchnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_float, c_float, c_int, c_int, c_void_p]),
+    "dc_batchnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dc_cosine_rows_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dc_cosine_rows_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "dc_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dc_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dc_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_dot_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -88,9 +97,9 @@ SIGNATURES = {
     "dc_vit_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "dc_text_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p]),
-    "dc_text_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p]),
+                                c_void_p, c_void_p]),
+    "dc_text_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
 }
 
 

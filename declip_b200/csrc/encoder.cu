@@ -65,6 +65,7 @@ struct TowerWs {
   int* row_idx;
   bf16 *rows, *rows_ln;
   float *mean_post, *rstd_post;
+  float *mean_f, *rstd_f;  // ln_final over every token (dense / MLM mode)
   // backward scratch
   bf16 *dxa, *dxb, *dqkv, *du, *dtmp, *dfeat, *drow, *drow2;
   size_t bytes;
@@ -106,6 +107,8 @@ static void carve(const dc_tower_cfg& c, void* base, TowerWs& w) {
   w.rows_ln = cv.take<bf16>(static_cast<size_t>(c.batch) * D);
   w.mean_post = cv.take<float>(c.batch);
   w.rstd_post = cv.take<float>(c.batch);
+  w.mean_f = cv.take<float>(M);
+  w.rstd_f = cv.take<float>(M);
   w.dxa = cv.take<bf16>(M * D);
   w.dxb = cv.take<bf16>(M * D);
   w.dqkv = cv.take<bf16>(M * 3 * D);
@@ -319,28 +322,34 @@ int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void*
 }
 
 int dc_text_forward(const dc_tower_cfg* cfg, const long long* ids, const void* const* w_bf16,
-                    const float* const* w_f32, void* workspace, float* features, dc_stream_t stream) {
+                    const float* const* w_f32, void* workspace, float* features, void* words_out, dc_stream_t stream) {
   DC_TRY(check_cfg(cfg));
   const dc_tower_cfg& c = *cfg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TowerWs w;
   carve(c, workspace, w);
-  const int D = c.width, NL = c.layers, E = c.embed_dim;
+  const int M = c.batch * c.seq_len, D = c.width, NL = c.layers, E = c.embed_dim;
   const float* const* xf = w_f32 + 8 * NL;
   DC_TRY(dc_text_embed(ids, xf[0], xf[1], w.xs[0], c.batch, c.seq_len, D, st));        // text_transformer.py:188-190
   DC_TRY(layers_forward(c, w, w_bf16, w_f32, st));
-  // ln_final is row-wise, so it commutes with the EOT row gather   text_transformer.py:194,203
   DC_TRY(dc_eot_index(ids, w.row_idx, c.batch, c.seq_len, st));
-  DC_TRY(dc_gather_rows(w.xs[NL], w.row_idx, w.rows, c.batch, D, st));
-  DC_TRY(dc_layernorm_fwd(w.rows, xf[2], xf[3], w.rows_ln, w.mean_post, w.rstd_post, c.batch, D, 1e-5f, st));
+  if (words_out != nullptr) {
+    // dense mode: ln_final on every token (words_feat), EOT rows gathered from it   text_transformer.py:194-203
+    DC_TRY(dc_layernorm_fwd(w.xs[NL], xf[2], xf[3], words_out, w.mean_f, w.rstd_f, M, D, 1e-5f, st));
+    DC_TRY(dc_gather_rows(words_out, w.row_idx, w.rows_ln, c.batch, D, st));
+  } else {
+    // ln_final is row-wise, so it commutes with the EOT row gather: normalise b rows instead of b*77
+    DC_TRY(dc_gather_rows(w.xs[NL], w.row_idx, w.rows, c.batch, D, st));
+    DC_TRY(dc_layernorm_fwd(w.rows, xf[2], xf[3], w.rows_ln, w.mean_post, w.rstd_post, c.batch, D, 1e-5f, st));
+  }
   dc_gemm_args a = gemm_args(w.rows_ln, D, 0, w_bf16[4 * NL + 0], D, 0, c.batch, E, D, DC_EPI_F32, features, E);
   a.bias = xf[4];
   return gemm_bf16(a, st);
 }
 
-int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float* dfeatures,
-                     const void* const* w_bf16, const float* const* w_f32, float* const* grads, void* workspace,
-                     dc_stream_t stream) {
+int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float* dfeatures, int dense,
+                     const void* dwords, const void* const* w_bf16, const float* const* w_f32, float* const* grads,
+                     void* workspace, dc_stream_t stream) {
   DC_TRY(check_cfg(cfg));
   const dc_tower_cfg& c = *cfg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -350,15 +359,26 @@ int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float*
   const float* const* xf = w_f32 + 8 * NL;
   float* const* xg = grads + 12 * NL;
   const bf16* wtp = static_cast<const bf16*>(w_bf16[4 * NL + 0]);
+  float* dcol_last = NL > 0 ? grads[12 * (NL - 1) + 9] : nullptr;   // c_proj.bias of the last layer
   DC_TRY(dc_cast_f32_bf16(dfeatures, w.dfeat, static_cast<size_t>(c.batch) * E, st));
   // text_projection: dW[E,D] += dfeat^T rows_ln ; db += colsum(dfeat) ; d rows_ln = dfeat W
   DC_TRY(linear_wgrad(w.dfeat, w.rows_ln, c.batch, E, D, xg[4], xg[5], st));
   DC_TRY(linear_dgrad(w.dfeat, wtp, c.batch, E, D, DC_EPI_BF16, w.drow, nullptr, st));
-  DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[2], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[2], xg[3],
-                          NL > 0 ? grads[12 * (NL - 1) + 9] : nullptr, c.batch, D, st));  // + c_proj.bias of the last layer
-  cudaError_t e = cudaMemsetAsync(w.dxa, 0, static_cast<size_t>(M) * D * sizeof(bf16), st);
-  if (e != cudaSuccess) return set_error_cuda("memset dx", e);
-  DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));
+  const size_t act_bytes = static_cast<size_t>(M) * D * sizeof(bf16);
+  if (dense) {
+    // d ln_final(all tokens) = dwords (+ EOT rows), then one LayerNorm backward over every token
+    cudaError_t e = dwords ? cudaMemcpyAsync(w.dtmp, dwords, act_bytes, cudaMemcpyDeviceToDevice, st)
+                           : cudaMemsetAsync(w.dtmp, 0, act_bytes, st);
+    if (e != cudaSuccess) return set_error_cuda("dense dwords copy", e);
+    DC_TRY(dc_add_rows(w.drow, w.row_idx, w.dtmp, c.batch, D, st));
+    DC_TRY(dc_layernorm_bwd(w.dtmp, w.xs[NL], xf[2], w.mean_f, w.rstd_f, nullptr, w.dxa, xg[2], xg[3], dcol_last, M, D, st));
+  } else {
+    DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[2], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[2], xg[3], dcol_last,
+                            c.batch, D, st));
+    cudaError_t e = cudaMemsetAsync(w.dxa, 0, act_bytes, st);
+    if (e != cudaSuccess) return set_error_cuda("memset dx", e);
+    DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));
+  }
   DC_TRY(layers_backward(c, w, w_bf16, w_f32, grads, st));
   return dc_text_embed_bwd(ids, w.dxa, xg[0], xg[1], c.batch, c.seq_len, D, st);
 }

@@ -422,7 +422,8 @@ __global__ void eot_index_kernel(const long long* __restrict__ ids, int* __restr
 // ------------------------------------------------------------------------------------------------
 // clip.py:129-130: y = x / (||x|| + eps); one warp per row.
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict__ x, bf16* __restrict__ y,
-                                                         float* __restrict__ inv_out, int n, int dim, float eps) {
+                                                         float* __restrict__ y32, float* __restrict__ inv_out, int n,
+                                                         int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
@@ -434,13 +435,17 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const float* __restrict
   }
   const float inv = 1.0f / (sqrtf(warp_sum(s)) + eps);
   if (lane == 0 && inv_out) inv_out[row] = inv;
-  bf16* yr = y + static_cast<size_t>(row) * dim;
   for (int c = lane * 4; c < dim; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    uint2 w;
-    w.x = pack_bf16x2(v.x * inv, v.y * inv);
-    w.y = pack_bf16x2(v.z * inv, v.w * inv);
-    *reinterpret_cast<uint2*>(yr + c) = w;
+    if (y != nullptr) {
+      uint2 w;
+      w.x = pack_bf16x2(v.x * inv, v.y * inv);
+      w.y = pack_bf16x2(v.z * inv, v.w * inv);
+      *reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * dim + c) = w;
+    }
+    if (y32 != nullptr)
+      *reinterpret_cast<float4*>(y32 + static_cast<size_t>(row) * dim + c) =
+          make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
   }
 }
 
@@ -488,12 +493,13 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 }
 
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
-                                                     int label0, float* __restrict__ loss_sum, int* __restrict__ top1,
+                                                     int label0, const long long* __restrict__ labels,
+                                                     float* __restrict__ loss_sum, int* __restrict__ top1,
                                                      int* __restrict__ top5, float* __restrict__ lse_out) {
   __shared__ float s_red[8];
   const int row = blockIdx.x;
   const float* z = logits + static_cast<size_t>(row) * ld;
-  const int label = label0 + row;
+  const int label = labels ? static_cast<int>(labels[row]) : label0 + row;
   float m = -INFINITY;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, z[c]);
   m = block_reduce(m, s_red, true);
@@ -518,12 +524,13 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
 // dlogits = (gscale_host * *gscale_dev) * (softmax(row) - onehot(label)); bf16 or fp32 output
 template <bool OUT_F32>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
-                                                     int label0, const float* __restrict__ lse,
+                                                     int label0, const long long* __restrict__ labels,
+                                                     const float* __restrict__ lse,
                                                      const float* __restrict__ gscale_dev, float gscale_host,
                                                      void* __restrict__ dl, int lddl) {
   const int row = blockIdx.x;
   const float* z = logits + static_cast<size_t>(row) * ld;
-  const int label = label0 + row;
+  const int label = labels ? static_cast<int>(labels[row]) : label0 + row;
   const float l = lse[row];
   const float gs = gscale_host * (gscale_dev ? *gscale_dev : 1.0f);
   const bool vec_ok = ((ld | lddl) & 1) == 0;
@@ -703,11 +710,11 @@ int dc_eot_index(const long long* ids, int* eot, int batch, int L, dc_stream_t s
   return 0;
 }
 
-int dc_l2norm_fwd(const float* x, void* y, float* inv, int n, int dim, float eps, dc_stream_t stream) {
+int dc_l2norm_fwd(const float* x, void* y, float* y_f32, float* inv, int n, int dim, float eps, dc_stream_t stream) {
   if (n <= 0) return 0;
   if (dim & 3) return set_error("l2norm: dim must be a multiple of 4");
-  l2norm_fwd_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(y), inv, n,
-                                                                                     dim, eps);
+  l2norm_fwd_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<bf16*>(y), y_f32,
+                                                                                     inv, n, dim, eps);
   DC_CHECK_LAUNCH("l2norm_fwd");
   return 0;
 }
@@ -720,25 +727,25 @@ int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, fl
   return 0;
 }
 
-int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, float* loss_sum, int* top1,
-                    int* top5, float* lse_out, dc_stream_t stream) {
+int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
+                    float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream) {
   if (rows <= 0) return 0;
-  if (label0 < 0 || label0 + rows > cols) return set_error("ce_strip: labels out of range");
-  ce_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, loss_sum, top1, top5,
-                                                                 lse_out);
+  if (labels == nullptr && (label0 < 0 || label0 + rows > cols)) return set_error("ce_strip: labels out of range");
+  ce_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, loss_sum, top1,
+                                                                 top5, lse_out);
   DC_CHECK_LAUNCH("ce_strip_fwd");
   return 0;
 }
 
-int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const float* lse,
-                    const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
+int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
+                    const float* lse, const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
                     dc_stream_t stream) {
   if (rows <= 0) return 0;
   if (out_f32)
-    ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, lse,
+    ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, lse,
                                                                          gscale_dev, gscale_host, dlogits, lddl);
   else
-    ce_bwd_kernel<false><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, lse,
+    ce_bwd_kernel<false><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, lse,
                                                                           gscale_dev, gscale_host, dlogits, lddl);
   DC_CHECK_LAUNCH("ce_strip_bwd");
   return 0;

@@ -34,7 +34,8 @@ def l2norm_fwd(x, eps, rows_pad=None):
         y = torch.zeros(rows_pad, d, device=x.device, dtype=torch.bfloat16)
     else:
         y = torch.empty(n, d, device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), _PTR(y.data_ptr()), None, n, d, eps, _stream()), "dc_l2norm_fwd")
+    _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), _PTR(y.data_ptr()), None, None, n, d, eps, _stream()),
+               "dc_l2norm_fwd")
     return y
 
 
@@ -154,10 +155,10 @@ class ClipInfoCE(torch.autograd.Function):
         cnt = torch.zeros(2, device=li.device, dtype=torch.int32)
         lse_i = torch.empty(b, device=li.device, dtype=torch.float32)
         lse_t = torch.empty(b, device=li.device, dtype=torch.float32)
-        _lib.check(lib.dc_ce_strip_fwd(_PTR(li.data_ptr()), li.stride(0), b, n, label0, _PTR(acc.data_ptr()),
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(li.data_ptr()), li.stride(0), b, n, label0, None, _PTR(acc.data_ptr()),
                                        _PTR(cnt.data_ptr()), _PTR(cnt.data_ptr() + 4), _PTR(lse_i.data_ptr()),
                                        _stream()), "dc_ce_strip_fwd")
-        _lib.check(lib.dc_ce_strip_fwd(_PTR(lt.data_ptr()), lt.stride(0), b, n, label0, _PTR(acc.data_ptr() + 4), None,
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(lt.data_ptr()), lt.stride(0), b, n, label0, None, _PTR(acc.data_ptr() + 4), None,
                                        None, _PTR(lse_t.data_ptr()), _stream()), "dc_ce_strip_fwd")
         ctx.save_for_backward(li, lt, lse_i, lse_t)
         ctx.label0 = label0
@@ -174,7 +175,316 @@ class ClipInfoCE(torch.autograd.Function):
         dli = torch.empty(b, n, device=li.device, dtype=torch.float32)
         dlt = torch.empty(b, n, device=li.device, dtype=torch.float32)
         for z, lse, d in ((li, lse_i, dli), (lt, lse_t, dlt)):
-            _lib.check(lib.dc_ce_strip_bwd(_PTR(z.data_ptr()), z.stride(0), b, n, ctx.label0, _PTR(lse.data_ptr()),
+            _lib.check(lib.dc_ce_strip_bwd(_PTR(z.data_ptr()), z.stride(0), b, n, ctx.label0, None, _PTR(lse.data_ptr()),
                                            _PTR(g.data_ptr()), 1.0 / (2.0 * b), _PTR(d.data_ptr()), d.stride(0), 1,
                                            _stream()), "dc_ce_strip_bwd")
         return dli, dlt, None, None
+
+
+# =====================================================================================================================
+# DeCLIP / FILIP building blocks (declip.py, loss.py, nnclr_modules) — each a thin autograd bridge over the C ABI.
+# =====================================================================================================================
+class L2Normalize(torch.autograd.Function):
+    """y = x / (||x|| + eps) as a real fp32 tensor (clip.py:129-130; DeCLIP returns these in ret_dict['features'])."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        lib = ops.lib_for(x)
+        x = x.float().contiguous()
+        n, d = x.shape
+        y = torch.empty_like(x)
+        _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), None, _PTR(y.data_ptr()), None, n, d, float(eps), _stream()),
+                   "dc_l2norm_fwd")
+        ctx.save_for_backward(x)
+        ctx.eps = float(eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return l2norm_bwd(dy.float().contiguous(), x, ctx.eps), None
+
+
+def _to_bf16_rows(x, rows_pad):
+    """fp32 [n,d] -> bf16 [rows_pad,d] (zero tail): operands of the strip GEMMs."""
+    n, d = x.shape
+    y = cast_bf16(x)
+    if rows_pad != n:
+        z = torch.zeros(rows_pad, d, device=x.device, dtype=torch.bfloat16)
+        z[:n] = y
+        return z
+    return y
+
+
+class StripLogits(torch.autograd.Function):
+    """Generalised logit strips over ALREADY-NORMALISED features: for each (i, j) in `pairs`,
+        strip = s * F_i(local rows) @ F_j(all ranks)^T          [b, N]
+    with one all-gather for all features (declip.py:264-269) and s = min(exp(logit_scale), 100) when `clamp`
+    (gradient flows as exp(logit_scale), clip.py:133-134) or the constant `scale_const` when logit_scale is None
+    (NT-Xent temperature).  Covers CLIP (2 strips), DeCLIP (8 + 4 NN strips, declip.py:271-300), NTXentLoss."""
+
+    @staticmethod
+    def forward(ctx, logit_scale, scale_const, gather, clamp, pairs, *feats):
+        nf = len(feats)
+        feats = [f.float().contiguous() for f in feats]
+        b, e = feats[0].shape
+        rank, world = dist_info()
+        gather = bool(gather) and world > 1
+        if gather and b % 8:
+            raise RuntimeError("declip_b200: per-rank batch must be a multiple of 8 when features are all-gathered")
+        bp = (b + 7) // 8 * 8
+        loc = torch.cat([_to_bf16_rows(f, bp) for f in feats], dim=1)          # [bp, nf*E] bf16
+        if gather:
+            allf = torch.empty(world * b, nf * e, device=loc.device, dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(allf, loc)
+        else:
+            allf = loc
+        n = world * b if gather else b
+        if logit_scale is not None:
+            s_raw = logit_scale.detach().float().exp().reshape(1)
+            s_used = torch.clamp(s_raw, max=100.0) if clamp else s_raw
+        else:
+            s_raw = s_used = torch.full((1,), float(scale_const), device=loc.device, dtype=torch.float32)
+        strips = []
+        for (i, j) in pairs:
+            strips.append(ops.gemm(loc[:b, i * e:(i + 1) * e], allf[:, j * e:(j + 1) * e], epilogue=ops.EPI_F32,
+                                   alpha_dev=s_used))
+        ctx.save_for_backward(loc, allf, s_raw, s_used, *strips)
+        ctx.meta = (nf, b, e, n, gather, pairs, logit_scale is not None, None)
+        n_pad = allf.shape[0]
+        return tuple(s[:, :n] if n_pad != n else s for s in strips)
+
+    @staticmethod
+    def backward(ctx, *dstrips):
+        loc, allf, s_raw, s_used = ctx.saved_tensors[:4]
+        strips = ctx.saved_tensors[4:]
+        nf, b, e, n, gather, pairs, has_ls, _ = ctx.meta
+        n_pad = allf.shape[0]
+        need = ctx.needs_input_grad[5:]
+        dloc = torch.zeros(nf, b, e, device=loc.device, dtype=torch.float32)
+        dall = torch.zeros(nf, n_pad, e, device=loc.device, dtype=torch.float32)
+        acc = torch.zeros(1, device=loc.device, dtype=torch.float32)
+        for k, (i, j) in enumerate(pairs):
+            ds = dstrips[k]
+            if ds is None:
+                continue
+            if n_pad != n:
+                pad = torch.zeros(b, n_pad, device=loc.device, dtype=torch.float32)
+                pad[:, :n] = ds
+                ds = pad
+            else:
+                ds = ds.contiguous().float()
+            ds16 = cast_bf16(ds)
+            if need[i]:    # dF_i(local) += s * dS F_j(all)                      (B read MN-major)
+                ops.gemm(ds16, allf[:, j * e:(j + 1) * e], b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC, out=dloc[i],
+                         alpha_dev=s_used)
+            if need[j]:    # dF_j(all) += s * dS^T F_i(local)                   (A, B read MN-major)
+                ops.gemm(ds16, loc[:b, i * e:(i + 1) * e], a_mn_major=True, b_mn_major=True,
+                         epilogue=ops.EPI_F32_ATOMIC, out=dall[j], alpha_dev=s_used)
+            if has_ls:
+                dot_into(ds, strips[k], acc)
+        if gather:
+            mine = torch.empty(nf, b, e, device=loc.device, dtype=torch.float32)
+            # reduce-scatter over ranks of every feature's gathered-side gradient == all_reduce + slice (clip.py:43-49)
+            send = dall.view(nf, -1, b, e).transpose(0, 1).contiguous()        # [W, nf, b, e]
+            dist.reduce_scatter_tensor(mine.view(-1), send.view(-1), op=dist.ReduceOp.SUM)
+            dloc = dloc + mine
+        else:
+            dloc = dloc + dall[:, :b]
+        grads = [dloc[i] if need[i] else None for i in range(nf)]
+        dls = (acc * (s_raw / s_used)).view(1) if has_ls else None
+        return (dls, None, None, None, None) + tuple(grads)
+
+
+class LinearF32(torch.autograd.Function):
+    """y = x W^T + b for the small fp32 heads (SimSiam projector/predictor, declip.py:48-60,107-112); bf16 tensor-core
+    GEMMs with fp32 I/O.  in/out features must be multiples of 8."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x16 = cast_bf16(x.float().contiguous())
+        w16 = cast_bf16(weight.contiguous())
+        y = ops.gemm(x16, w16, bias=bias, epilogue=ops.EPI_F32)
+        ctx.save_for_backward(x16, w16)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        dy16 = cast_bf16(dy.float().contiguous())
+        dx = ops.gemm(dy16, w16, b_mn_major=True, epilogue=ops.EPI_F32) if ctx.needs_input_grad[0] else None
+        dw = ops.gemm(dy16, x16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)
+        db = ops.colsum(dy16) if ctx.has_bias else None
+        return dx, dw, db
+
+
+class BatchNorm1dF(torch.autograd.Function):
+    """nn.BatchNorm1d (+ optional fused ReLU) — declip.py:49-60,108-110.  Batch statistics are PER RANK, as in the
+    reference (nn.BatchNorm1d, not SyncBN)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, relu, eps, momentum):
+        lib = ops.lib_for(x)
+        x = x.float().contiguous()
+        rows, c = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(c, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(c, device=x.device, dtype=torch.float32)
+        _lib.check(lib.dc_batchnorm_fwd(_PTR(x.data_ptr()), _PTR(gamma.data_ptr()), _PTR(beta.data_ptr()),
+                                        _PTR(y.data_ptr()), _PTR(mean.data_ptr()), _PTR(rstd.data_ptr()),
+                                        _PTR(running_mean.data_ptr()), _PTR(running_var.data_ptr()), rows, c, float(eps),
+                                        float(momentum), int(training), int(relu), _stream()), "dc_batchnorm_fwd")
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.training, ctx.relu = bool(training), bool(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        lib = ops.lib_for(x)
+        rows, c = x.shape
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(x)
+        dg = torch.zeros(c, device=x.device, dtype=torch.float32)
+        db = torch.zeros(c, device=x.device, dtype=torch.float32)
+        _lib.check(lib.dc_batchnorm_bwd(_PTR(dy.data_ptr()), _PTR(x.data_ptr()), _PTR(y.data_ptr()), _PTR(gamma.data_ptr()),
+                                        _PTR(mean.data_ptr()), _PTR(rstd.data_ptr()), _PTR(dx.data_ptr()),
+                                        _PTR(dg.data_ptr()), _PTR(db.data_ptr()), rows, c, int(ctx.training), int(ctx.relu),
+                                        _stream()), "dc_batchnorm_bwd")
+        return dx, dg, db, None, None, None, None, None, None
+
+
+class CosineMean(torch.autograd.Function):
+    """D(p, z) = mean_r cos(p_r, stopgrad(z_r)) — loss_functions/loss.py:52-58."""
+
+    @staticmethod
+    def forward(ctx, p, z):
+        lib = ops.lib_for(p)
+        p = p.float().contiguous()
+        z = z.detach().float().contiguous()
+        n, d = p.shape
+        cosv = torch.empty(n, device=p.device, dtype=torch.float32)
+        _lib.check(lib.dc_cosine_rows_fwd(_PTR(p.data_ptr()), _PTR(z.data_ptr()), _PTR(cosv.data_ptr()), n, d, _stream()),
+                   "dc_cosine_rows_fwd")
+        ctx.save_for_backward(p, z)
+        return cosv.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        p, z = ctx.saved_tensors
+        lib = ops.lib_for(p)
+        n, d = p.shape
+        grow = (g.float() / n).expand(n).contiguous()
+        dp = torch.empty_like(p)
+        _lib.check(lib.dc_cosine_rows_bwd(_PTR(p.data_ptr()), _PTR(z.data_ptr()), _PTR(grow.data_ptr()), 1.0,
+                                          _PTR(dp.data_ptr()), n, d, _stream()), "dc_cosine_rows_bwd")
+        return dp, None
+
+
+class RowCE(torch.autograd.Function):
+    """mean_r CE(logits[r, :cols], labels[r]) with an int64 label array (MLM head, declip.py:330-333)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, cols):
+        lib = ops.lib_for(logits)
+        n = logits.shape[0]
+        acc = torch.zeros(1, device=logits.device, dtype=torch.float32)
+        lse = torch.empty(n, device=logits.device, dtype=torch.float32)
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(logits.data_ptr()), logits.stride(0), n, cols, 0, _PTR(labels.data_ptr()),
+                                       _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
+                   "dc_ce_strip_fwd")
+        ctx.save_for_backward(logits, labels, lse)
+        ctx.cols = cols
+        return acc[0] / n
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse = ctx.saved_tensors
+        lib = ops.lib_for(logits)
+        n = logits.shape[0]
+        g = g.contiguous().float().reshape(1)
+        d = torch.zeros_like(logits)
+        _lib.check(lib.dc_ce_strip_bwd(_PTR(logits.data_ptr()), logits.stride(0), n, ctx.cols, 0, _PTR(labels.data_ptr()),
+                                       _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(d.data_ptr()), d.stride(0), 1,
+                                       _stream()), "dc_ce_strip_bwd")
+        return d, None, None
+
+
+class MaskedLMHead(torch.autograd.Function):
+    """text_label_predictor on the masked positions only, + cross-entropy — declip.py:326-334.  The reference runs the
+    512 -> 49409 Linear on all B*77 tokens and then boolean-masks (7.8 GB of logits at b=512); gathering the masked
+    rows first is mathematically identical.  words bf16 [B*L, D]; rows int32 [n] (masked token rows); labels int64 [n]."""
+
+    @staticmethod
+    def forward(ctx, words, rows, labels, weight, bias):
+        lib = ops.lib_for(words)
+        n = rows.numel()
+        v, d = weight.shape
+        vp = (v + 7) // 8 * 8
+        w16 = torch.zeros(vp, d, device=words.device, dtype=torch.bfloat16)
+        _lib.check(lib.dc_cast_f32_bf16(_PTR(weight.data_ptr()), _PTR(w16.data_ptr()), weight.numel(), _stream()),
+                   "dc_cast_f32_bf16")
+        bpad = torch.zeros(vp, device=words.device, dtype=torch.float32)
+        bpad[:v] = bias
+        x = torch.empty(n, d, device=words.device, dtype=torch.bfloat16)
+        _lib.check(lib.dc_gather_rows(_PTR(words.data_ptr()), _PTR(rows.data_ptr()), _PTR(x.data_ptr()), n, d, _stream()),
+                   "dc_gather_rows")
+        logits = ops.gemm(x, w16, bias=bpad, epilogue=ops.EPI_F32)                       # [n, vp] fp32
+        acc = torch.zeros(1, device=words.device, dtype=torch.float32)
+        lse = torch.empty(n, device=words.device, dtype=torch.float32)
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(logits.data_ptr()), logits.stride(0), n, v, 0, _PTR(labels.data_ptr()),
+                                       _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
+                   "dc_ce_strip_fwd")
+        ctx.save_for_backward(x, rows, labels, w16, logits, lse)
+        ctx.shape = (words.shape[0], v, vp, d)
+        return acc[0] / n
+
+    @staticmethod
+    def backward(ctx, g):
+        x, rows, labels, w16, logits, lse = ctx.saved_tensors
+        lib = ops.lib_for(x)
+        m, v, vp, d = ctx.shape
+        n = x.shape[0]
+        g = g.contiguous().float().reshape(1)
+        dl = torch.zeros(n, vp, device=x.device, dtype=torch.bfloat16)
+        _lib.check(lib.dc_ce_strip_bwd(_PTR(logits.data_ptr()), logits.stride(0), n, v, 0, _PTR(labels.data_ptr()),
+                                       _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(dl.data_ptr()), dl.stride(0),
+                                       0, _stream()), "dc_ce_strip_bwd")
+        dw = ops.gemm(dl, x, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)[:v]     # [v, d]
+        db = ops.colsum(dl)[:v]
+        dx = ops.gemm(dl, w16, b_mn_major=True, epilogue=ops.EPI_BF16)                             # [n, d] bf16
+        dwords = torch.zeros(m, d, device=x.device, dtype=torch.bfloat16)
+        _lib.check(lib.dc_scatter_rows(_PTR(dx.data_ptr()), _PTR(rows.data_ptr()), _PTR(dwords.data_ptr()), n, d, _stream()),
+                   "dc_scatter_rows")
+        return dwords, None, None, dw, db
+
+
+def nn_lookup(query, bank, bank16):
+    """Top-1 nearest neighbour of each query row in the memory bank (cosine similarity) —
+    nnclr_modules/nn_memory_bank.py:54-64.  query fp32 [b,d]; bank fp32 [size,d] (raw rows, returned un-normalised as in
+    the reference); bank16 bf16 [size,d] = F.normalize(bank).  No gradient (the reference detaches)."""
+    lib = ops.lib_for(query)
+    query = query.detach().float().contiguous()
+    b, d = query.shape
+    q16 = torch.empty(b, d, device=query.device, dtype=torch.bfloat16)
+    _lib.check(lib.dc_l2norm_fwd(_PTR(query.data_ptr()), _PTR(q16.data_ptr()), None, None, b, d, 1e-12, _stream()),
+               "dc_l2norm_fwd")
+    sim = ops.gemm(q16, bank16, epilogue=ops.EPI_F32)                                    # [b, size]
+    idx = torch.empty(b, device=query.device, dtype=torch.int32)
+    _lib.check(lib.dc_argmax_rows(_PTR(sim.data_ptr()), sim.stride(0), b, sim.shape[1], _PTR(idx.data_ptr()), _stream()),
+               "dc_argmax_rows")
+    out = torch.empty(b, d, device=query.device, dtype=torch.float32)
+    _lib.check(lib.dc_gather_rows_f32(_PTR(bank.data_ptr()), _PTR(idx.data_ptr()), _PTR(out.data_ptr()), b, d, _stream()),
+               "dc_gather_rows_f32")
+    return out, idx
+
+
+def normalize_rows_bf16(x, eps=1e-12):
+    """bf16 F.normalize(x, dim=1) of fp32 rows (memory-bank shadow)."""
+    lib = ops.lib_for(x)
+    x = x.float().contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), _PTR(y.data_ptr()), None, None, x.shape[0], x.shape[1], eps, _stream()),
+               "dc_l2norm_fwd")
+    return y

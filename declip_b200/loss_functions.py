@@ -25,3 +25,72 @@ class ClipInfoCELoss(_Loss):
         tensors (no host sync)."""
         rows = float(self.stats["rows"])
         return self.stats["top1_count"].float() * (100.0 / rows), self.stats["top5_count"].float() * (100.0 / rows)
+
+
+class SimsiamLoss(torch.nn.Module):
+    """loss_functions/loss.py:60-84: -0.5 * (D(p1, z2) + D(p2, z1)), D = mean cosine with stop-gradient on z."""
+
+    def __init__(self, symmetry=True):
+        super().__init__()
+        self.symmetry = symmetry
+
+    def forward(self, p1, z1, p2, z2, minimize_loss=False):
+        if not self.symmetry or minimize_loss:
+            raise NotImplementedError("declip_b200: only the symmetric SimSiam loss of the reference configs is built")
+        return -0.5 * (F_.CosineMean.apply(p1, z2) + F_.CosineMean.apply(p2, z1))
+
+
+class StripCE(torch.autograd.Function):
+    """mean_r CE(logits[r], label0 + r) on one strip."""
+
+    @staticmethod
+    def forward(ctx, logits, label0):
+        import ctypes
+        from . import _lib, ops
+        lib = ops.lib_for(logits)
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        b, n = logits.shape
+        acc = torch.zeros(1, device=logits.device, dtype=torch.float32)
+        lse = torch.empty(b, device=logits.device, dtype=torch.float32)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = ctypes.c_void_p
+        _lib.check(lib.dc_ce_strip_fwd(P(logits.data_ptr()), logits.stride(0), b, n, label0, None, P(acc.data_ptr()), None,
+                                       None, P(lse.data_ptr()), st), "dc_ce_strip_fwd")
+        ctx.save_for_backward(logits, lse)
+        ctx.label0 = label0
+        return acc[0] / b
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from . import _lib, ops
+        logits, lse = ctx.saved_tensors
+        lib = ops.lib_for(logits)
+        b, n = logits.shape
+        g = g.contiguous().float().reshape(1)
+        d = torch.empty(b, n, device=logits.device, dtype=torch.float32)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = ctypes.c_void_p
+        _lib.check(lib.dc_ce_strip_bwd(P(logits.data_ptr()), logits.stride(0), b, n, ctx.label0, None, P(lse.data_ptr()),
+                                       P(g.data_ptr()), 1.0 / b, P(d.data_ptr()), d.stride(0), 1, st), "dc_ce_strip_bwd")
+        return d, None
+
+
+class NTXentLoss(torch.nn.Module):
+    """loss_functions/nt_xent_ConVIRT.py:4-86: local b x b image-text NT-Xent with soft targets = identity:
+    alpha * CE(zi zj^T / T) + (1 - alpha) * CE(zj zi^T / T).  Evaluated every DeCLIP step by the reference solver
+    (declip_solver.py:486-488) but only enters the loss for clip_simsiam_loss_weight.type == 'convirt'."""
+
+    def __init__(self, batch_size, temperature=0.1, use_cosine_similarity=True, alpha_weight=0.75):
+        super().__init__()
+        self.batch_size = batch_size
+        self.temperature = temperature
+        self.alpha_weight = alpha_weight
+
+    def forward(self, zis, zjs, norm=True, weights=1.0):
+        if norm:
+            zis = F_.L2Normalize.apply(zis, 1e-12)
+            zjs = F_.L2Normalize.apply(zjs, 1e-12)
+        ab, ba = F_.StripLogits.apply(None, 1.0 / self.temperature, False, False, ((0, 1), (1, 0)), zis, zjs)
+        return self.alpha_weight * StripCE.apply(ab, 0) + (1 - self.alpha_weight) * StripCE.apply(ba, 0)

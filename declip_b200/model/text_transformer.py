@@ -66,8 +66,6 @@ class TextTransformer(nn.Module):
 
     def tokenize(self, texts, context_length=77, return_length=False, mask_type=None):
         """text_transformer.py:144-180.  Needs the BPE vocabulary file (not shipped with the reference)."""
-        if mask_type is not None:
-            raise NotImplementedError("declip_b200: MLM masking (DeCLIP) not built yet")
         if self.tokenizer is None:
             raise RuntimeError("declip_b200: no BPE tokenizer loaded (bpe_path=%r). Pass a pre-tokenised LongTensor "
                                "[B,%d] instead of strings." % (self.bpe_path, self.context_length))
@@ -83,18 +81,34 @@ class TextTransformer(nn.Module):
         return result
 
     def forward(self, text, mask_type=None, return_dense=False):
-        if mask_type is not None or return_dense:
-            raise NotImplementedError("declip_b200: mask_type / return_dense (DeCLIP MLM, FILIP) not built yet")
-        if torch.is_tensor(text):
+        """text: List[str] (reference API) | LongTensor ids [B,77] | (masked_ids, labels) when already MLM-masked.
+        Returns x [B,E]; with mask_type: (x, words_feat, labels); with return_dense: (x, words_feat)
+        (text_transformer.py:183-274).  words_feat is bf16 [B,77,D] (ln_final of every token)."""
+        labels = None
+        if isinstance(text, (tuple, list)) and len(text) == 2 and torch.is_tensor(text[0]):
+            ids, labels = text
+        elif torch.is_tensor(text):
             ids = text
         else:
             ids = self.tokenize(text, context_length=self.context_length)
+        if mask_type is not None and labels is None:
+            if mask_type != 'MLM':
+                raise NotImplementedError(mask_type)
+            from .text_utils import mask_tokens_batch
+            ids, labels = mask_tokens_batch(ids)                                   # text_transformer.py:154-162
         if ids.dim() != 2 or ids.shape[1] != self.context_length:
             raise ValueError("expected token ids [B,%d], got %s" % (self.context_length, tuple(ids.shape)))
         dev = self.positional_embedding.device
         if ids.device != dev:
             ids = ids.to(dev, non_blocking=True)                                   # text_transformer.py:188
-        return run_tower(self._rt, ids)
+        dense = mask_type is not None or return_dense
+        if not dense:
+            return run_tower(self._rt, ids)
+        x, words = run_tower(self._rt, ids, dense=True)
+        words = words.view(ids.shape[0], self.context_length, -1)
+        if mask_type is not None:
+            return x, words, labels
+        return x, words
 
 
 def text_transformers(**kwargs):

@@ -128,7 +128,7 @@ class TowerRuntime:
         return torch.empty(nbytes, device=dev, dtype=torch.uint8)
 
     # ------------------------------------------------------------------ executors
-    def forward(self, inp, params):
+    def forward(self, inp, params, dense=False):
         self._prepare(params)
         self.refresh_shadows(params)
         batch = inp.shape[0]
@@ -144,12 +144,19 @@ class TowerRuntime:
         else:
             if inp.dtype != torch.int64 or not inp.is_contiguous():
                 inp = inp.long().contiguous()
+            words = None
+            if dense:   # ln_final of every token (words_feat, text_transformer.py:194-201)
+                words = torch.empty(batch * self.seq_len, self.width, device=inp.device, dtype=torch.bfloat16)
             _lib.check(self.lib.dc_text_forward(ctypes.byref(cfg), _PTR(inp.data_ptr()), self.w_bf16, self.w_f32,
-                                                _PTR(ws.data_ptr()), _PTR(feats.data_ptr()), _stream()),
+                                                _PTR(ws.data_ptr()), _PTR(feats.data_ptr()),
+                                                _PTR(words.data_ptr()) if dense else None, _stream()),
                        "dc_text_forward")
-        return feats, inp, cfg, ws
+            return feats, inp, cfg, ws, words
+        if dense:
+            raise NotImplementedError("declip_b200: dense ViT output (FILIP) not built yet")
+        return feats, inp, cfg, ws, None
 
-    def backward(self, cfg, inp, ws, dfeats, params):
+    def backward(self, cfg, inp, ws, dfeats, params, dense=False, dwords=None):
         """Accumulates parameter gradients straight into `p.grad` (views of one flat fp32 buffer per tower, the
         DDP/"main_grad" pattern), so the gradient all-reduce is a single NCCL call per tower and a module that is
         run several times per step accumulates correctly.  Ownership rules per parameter:
@@ -184,12 +191,17 @@ class TowerRuntime:
             for n, v in zip(self.grad_names, views):
                 if params[n].requires_grad and params[n].grad is None:
                     v.zero_()
+        if dfeats is None:
+            dfeats = torch.zeros(cfg.batch, self.embed_dim, device=ws.device, dtype=torch.float32)
         dfeats = dfeats.float().contiguous()
+        if dwords is not None:
+            dwords = dwords.to(torch.bfloat16).contiguous()
         if self.kind == "vit":
             _lib.check(self.lib.dc_vit_backward(ctypes.byref(cfg), _PTR(dfeats.data_ptr()), self.w_bf16, self.w_f32, ptrs,
                                                 _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
         else:
             _lib.check(self.lib.dc_text_backward(ctypes.byref(cfg), _PTR(inp.data_ptr()), _PTR(dfeats.data_ptr()),
+                                                 int(dense), _PTR(dwords.data_ptr()) if dwords is not None else None,
                                                  self.w_bf16, self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()),
                        "dc_text_backward")
         if tmp is not None:
@@ -210,29 +222,33 @@ class TowerRuntime:
 
 
 class _TowerFunction(torch.autograd.Function):
-    """features = tower(inp; params).  One C-ABI call forward, one backward.  Parameter gradients are written
-    into p.grad by the runtime (see TowerRuntime.backward); autograd only carries d(features)."""
+    """features [, words] = tower(inp; params).  One C-ABI call forward, one backward.  Parameter gradients are
+    written into p.grad by the runtime (see TowerRuntime.backward); autograd only carries d(features), d(words)."""
 
     @staticmethod
-    def forward(ctx, rt, inp, anchor):
+    def forward(ctx, rt, inp, anchor, dense):
         params = rt._params()
-        feats, inp_used, cfg, ws = rt.forward(inp, params)
-        ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params = rt, cfg, inp_used, ws, params
+        feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)
+        ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense = rt, cfg, inp_used, ws, params, dense
+        if dense:
+            return feats, words
         return feats
 
     @staticmethod
-    def backward(ctx, dfeats):
-        ctx.rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params)
+    def backward(ctx, dfeats, dwords=None):
+        ctx.rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords)
         ctx.ws = None
-        return None, None, None
+        return None, None, None, None
 
 
-def run_tower(rt, inp):
+def run_tower(rt, inp, dense=False):
     """Run the tower through autograd (training) or directly (no_grad / eval).  `anchor` is any trainable
-    parameter: it makes the output require grad so backward is invoked."""
+    parameter: it makes the output require grad so backward is invoked.  dense=True also returns ln_final of every
+    token as bf16 [B*L, D]."""
     params = rt._params()
     if torch.is_grad_enabled():
         anchor = next((p for p in params.values() if p.requires_grad), None)
         if anchor is not None:
-            return _TowerFunction.apply(rt, inp, anchor)
-    return rt.forward(inp, params)[0]
+            return _TowerFunction.apply(rt, inp, anchor, dense)
+    out = rt.forward(inp, params, dense)
+    return (out[0], out[4]) if dense else out[0]

@@ -128,24 +128,48 @@ int dc_scatter_rows(const void* src, const int* idx, void* dst, int n, int width
 int dc_eot_index(const long long* ids, int* eot, int batch, int L, dc_stream_t stream);
 
 /* ------------------------------------------------------------------ contrastive head
- * clip.py:129-130: y = x / (||x|| + eps) row-wise; x fp32 [n,dim] -> y bf16, inv fp32 [n] = 1/(||x||+eps). */
-int dc_l2norm_fwd(const float* x, void* y, float* inv, int n, int dim, float eps, dc_stream_t stream);
+ * clip.py:129-130: y = x / (||x|| + eps) row-wise; x fp32 [n,dim] -> y bf16 and/or y_f32 (either may be
+ * NULL), inv fp32 [n] = 1/(||x||+eps) (may be NULL). */
+int dc_l2norm_fwd(const float* x, void* y, float* y_f32, float* inv, int n, int dim, float eps, dc_stream_t stream);
 /* dx(fp32) = inv*dy - x * <dy,x> * inv^2 / ||x||  with inv = 1/(||x|| + eps); dy, x fp32 [n,dim]. */
 int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, float eps, dc_stream_t stream);
 /* loss.py:40-50 (ClipInfoCELoss) on one logit strip, fused with misc.py:415-428 (accuracy top-1/top-5):
- * logits fp32 [rows,cols] (row stride ld), label[r] = label0 + r.
+ * logits fp32 [rows,cols] (row stride ld), label[r] = labels ? labels[r] : label0 + r  (the int64 `labels`
+ * array serves the DeCLIP masked-language-model head, declip.py:326-334).
  *   *loss_sum += sum_r (lse_r - logit[r,label_r])      (fp32 atomic; caller zeroes and divides by rows)
  *   *top1/*top5 += #{r : #(logit[r,:] > logit[r,label_r]) < 1 / < 5}   (may be NULL)
  *   lse_out[r] = log-sum-exp of row r (saved for backward). */
-int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, float* loss_sum, int* top1,
-                    int* top5, float* lse_out, dc_stream_t stream);
+int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
+                    float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream);
 /* dlogits([rows,cols], row stride lddl; bf16, or fp32 when out_f32) =
  *   gscale_host * (*gscale_dev) * (softmax(row) - onehot(label));  gscale_dev may be NULL (treated as 1). */
-int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const float* lse,
-                    const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
+int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
+                    const float* lse, const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
                     dc_stream_t stream);
 /* *out += sum_i a[i]*b[i]  (fp32; used for d logit_scale = exp(ls)/s * sum dlogits*logits, clip.py:133-141) */
 int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t stream);
+
+/* ------------------------------------------------------------------ DeCLIP heads (all fp32, [batch, <= 1024])
+ * nn.BatchNorm1d (+ fused ReLU) of the SimSiam projector / predictor MLPs — declip.py:33-130.  training: batch
+ * statistics, running stats updated with momentum (unbiased variance) when non-NULL; eval: running statistics. */
+int dc_batchnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* save_mean,
+                     float* save_rstd, float* running_mean, float* running_var, int rows, int channels, float eps,
+                     float momentum, int training, int relu, dc_stream_t stream);
+/* dgamma/dbeta are ACCUMULATED; `y` is the forward output (its sign is the ReLU mask). */
+int dc_batchnorm_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* save_mean,
+                     const float* save_rstd, float* dx, float* dgamma, float* dbeta, int rows, int channels,
+                     int training, int relu, dc_stream_t stream);
+/* SimsiamLoss D(p, z) = mean_r cos(p_r, stopgrad z_r) — loss_functions/loss.py:52-84.
+ * fwd: cosv[r]; bwd: dp[r,:] = gscale * grow[r] * d cos / d p  (grow may be NULL = 1). */
+int dc_cosine_rows_fwd(const float* p, const float* z, float* cosv, int n, int dim, dc_stream_t stream);
+int dc_cosine_rows_bwd(const float* p, const float* z, const float* grow, float gscale, float* dp, int n, int dim,
+                       dc_stream_t stream);
+/* Nearest-neighbour memory bank lookup — nnclr_modules/nn_memory_bank.py:42-65: idx[r] = argmax_c sim[r,c]
+ * (top-1), then dst[i,:] = bank[idx[i],:] (fp32 rows). */
+int dc_argmax_rows(const float* x, int ld, int rows, int cols, int* idx, dc_stream_t stream);
+int dc_gather_rows_f32(const float* src, const int* idx, float* dst, int n, int width, dc_stream_t stream);
+/* dst[idx[i],:] += src[i,:] (bf16 rows, distinct idx): EOT-row gradient added into the dense ln_final gradient. */
+int dc_add_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream);
 
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.
@@ -164,11 +188,14 @@ int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sampl
                    dc_stream_t stream);
 int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* const* w_bf16,
                     const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream);
+/* words_out (bf16 [batch*L, width], may be NULL): ln_final applied to EVERY token — the `words_feat` that
+ * TextTransformer.forward returns with mask_type / return_dense (text_transformer.py:194-201).  When it was requested
+ * in forward, backward must be called with dense=1 and dwords (bf16 [batch*L, width] or NULL = zero). */
 int dc_text_forward(const dc_tower_cfg* cfg, const long long* ids, const void* const* w_bf16,
-                    const float* const* w_f32, void* workspace, float* features, dc_stream_t stream);
-int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float* dfeatures,
-                     const void* const* w_bf16, const float* const* w_f32, float* const* grads, void* workspace,
-                     dc_stream_t stream);
+                    const float* const* w_f32, void* workspace, float* features, void* words_out, dc_stream_t stream);
+int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float* dfeatures, int dense,
+                     const void* dwords, const void* const* w_bf16, const float* const* w_f32, float* const* grads,
+                     void* workspace, dc_stream_t stream);
 
 #ifdef __cplusplus
 }

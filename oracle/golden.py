@@ -11,6 +11,22 @@ CASES = {
     "clip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=1),
     "clip_vitb32_l12_b32": dict(batch=32, v_layers=12, t_layers=12, embed_dim=512, seed=0),   # BASELINE configs[0]
 }
+DECLIP_CASES = {
+    "declip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=2, nn_size=1024),
+}
+
+
+def declip_inputs(c):
+    """Synthetic DeCLIP batch for a case: (state_dict, images[B,6,H,W], mlm_ids, mlm_labels, ids_aug, bank[dim,size])."""
+    from . import synth
+    sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"], t_layers=c["t_layers"])
+    sd.update(synth.declip_extra_state_dict(seed=c["seed"], feature_dim=c["embed_dim"]))
+    images = synth.synth_images(c["batch"], seed=c["seed"], channels=6)
+    ids = synth.synth_token_ids(c["batch"], seed=c["seed"])
+    mlm_ids, mlm_labels = synth.synth_mlm(ids, seed=c["seed"])
+    ids_aug = synth.synth_token_ids(c["batch"], seed=c["seed"] + 100)
+    bank = synth.synth_bank(c["embed_dim"], c["nn_size"], seed=c["seed"])
+    return sd, images, mlm_ids, mlm_labels, ids_aug, bank
 
 
 def sample_index(numel):

@@ -106,3 +106,45 @@ def reference_clip_step(sd, images, ids, embed_dim=512, v_layers=12, t_layers=12
         loss.backward()
         out["grads"] = {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}
     return out, model
+
+
+def _ensure_pg():
+    """The reference AllGather calls torch.distributed even at world size 1 (clip.py:36): a 1-rank gloo group."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import tempfile as _tf
+        store = dist.FileStore(os.path.join(_tf.mkdtemp(), "pg"), 1)
+        dist.init_process_group("gloo", store=store, rank=0, world_size=1)
+
+
+def reference_declip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_by_size, embed_dim=512, v_layers=12,
+                          t_layers=12, weights=None):
+    """Reference declip_vitb32 (MLM + NN bank) forward, the solver's loss composition (declip_solver.py:435-517,
+    restated by oracle.declip_ref.declip_loss on the reference's OWN outputs) and backward.  CPU fp32."""
+    setup()
+    _ensure_pg()
+    from prototype.model import model_entry
+    from . import declip_ref
+    nn_size = bank_dim_by_size.shape[1]
+    cfg = dict(type="declip_vitb32", kwargs=dict(
+        image_encode=dict(embed_dim=embed_dim, layers=v_layers),
+        text_encode=dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=embed_dim, transformer_layers=t_layers),
+        clip=dict(use_allgather=True, text_mask_type="MLM", return_nn_bank=True, feature_dim=embed_dim, nn_size=nn_size)))
+    model = model_entry(cfg).train()
+    model.load_state_dict(sd, strict=True)
+    model.nn_replacer_text.bank = bank_dim_by_size.clone()
+    model.nn_replacer_text.bank_ptr = torch.LongTensor([0])
+
+    def _tok(texts, context_length=77, return_length=False, mask_type=None):
+        return (mlm_ids.clone(), mlm_labels.clone()) if mask_type is not None else ids_aug
+    model.encode_text.tokenize = _tok
+    B = images6.shape[0]
+    out = model({"images": images6, "captions": [["x"]] * B}, return_dict=True)
+    loss, parts = declip_ref.declip_loss(out, weights or declip_ref.LOSS_WEIGHTS)
+    loss.backward()
+    res = {"loss": loss.detach(), "parts": {k: v.detach() for k, v in parts.items()},
+           "out": out, "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None},
+           "stats": {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k},
+           "bank": model.nn_replacer_text.bank.clone(), "bank_ptr": int(model.nn_replacer_text.bank_ptr)}
+    return res, model

@@ -97,3 +97,51 @@ def synth_token_ids(batch, seed=0, ctx=77, vocab=VOCAB):
         ids[b, 1:1 + n] = body[b, :n]
         ids[b, 1 + n] = EOT
     return ids
+
+
+def declip_extra_state_dict(seed=0, feature_dim=512, t_width=512, vocab=VOCAB):
+    """Extra DECLIP keys (declip.py:48-60,107-112,171): SimSiam projector / predictor (+ BatchNorm buffers) and the
+    MLM head `text_label_predictor`."""
+    sd = {}
+
+    def lin(name, out_f, in_f):
+        sd[name + ".weight"] = _randn(name + ".weight", seed, (out_f, in_f), in_f ** -0.5)
+        sd[name + ".bias"] = _randn(name + ".bias", seed, (out_f,), 0.02)
+
+    def bn(name, c):
+        sd[name + ".weight"] = 1.0 + _randn(name + ".weight", seed, (c,), 0.1)
+        sd[name + ".bias"] = _randn(name + ".bias", seed, (c,), 0.02)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    lin("projector.linear1", 1024, feature_dim); bn("projector.bn1", 1024)
+    lin("projector.linear2", 1024, 1024); bn("projector.bn2", 1024)
+    lin("projector.linear3", 1024, 1024); bn("projector.bn3", 1024)
+    lin("predictor.linear1", 512, 1024); bn("predictor.bn1", 512)
+    lin("predictor.layer2", 1024, 512)
+    lin("text_label_predictor", vocab, t_width)
+    return sd
+
+
+def synth_bank(dim=512, size=1024, seed=0):
+    """NN memory bank in the reference layout [dim, size], unit-norm columns (memory_bank.py:66-67)."""
+    b = torch.randn(dim, size, generator=_gen("bank", seed))
+    return torch.nn.functional.normalize(b, dim=0)
+
+
+def synth_mlm(ids, seed=0):
+    """Deterministic BERT-style masking of synthetic ids (mask_tokens.py:5-29 distribution): returns (masked_ids, labels)."""
+    g = _gen("mlm", seed)
+    ids = ids.clone()
+    B, L = ids.shape
+    lens = ids.argmax(1) + 1
+    pos = torch.arange(L).unsqueeze(0)
+    valid = (pos < lens.unsqueeze(1)) & (ids != SOT) & (ids != EOT) & (ids != MASK)
+    masked = (torch.rand(B, L, generator=g) < 0.15) & valid
+    labels = torch.where(masked, ids, torch.full_like(ids, -100))
+    r = torch.rand(B, L, generator=g)
+    ids[masked & (r < 0.8)] = MASK
+    rnd = masked & (r >= 0.8) & (r < 0.9)
+    ids[rnd] = torch.randint(0, VOCAB, (B, L), generator=g)[rnd]
+    return ids, labels

@@ -1,0 +1,158 @@
+"""GPU parity of the DeCLIP path (BASELINE configs[2]: multi-view + SimSiam + NN + MLM) against the golden vectors
+of the reference's own DECLIP module and the oracle restatement; plus op-level checks of the DeCLIP head kernels.
+Tolerances (bf16 storage / fp32 accumulate): total loss |d| <= 3e-2, parts as stated, gradient cosine >= 0.97."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-20)).item()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def test_batchnorm_linear_cosine_ops(cuda_dev):
+    from declip_b200 import functions as F_
+    torch.manual_seed(0)
+    x = torch.randn(64, 512, device=cuda_dev, requires_grad=True)
+    lin = torch.nn.Linear(512, 1024).to(cuda_dev)
+    bn = torch.nn.BatchNorm1d(1024).to(cuda_dev).train()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.1)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    y = F_.LinearF32.apply(x, lin.weight, lin.bias)
+    y = F_.BatchNorm1dF.apply(y, bn.weight, bn.bias, rm, rv, True, True, bn.eps, bn.momentum)
+    z = torch.randn(64, 1024, device=cuda_dev)
+    loss = F_.CosineMean.apply(y, z)
+    loss.backward()
+    g_x, g_w, g_b, g_g = x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), bn.weight.grad.clone()
+    x.grad = None
+    lin.zero_grad()
+    bn.zero_grad()
+    yr = torch.relu(bn(lin(x)))
+    zr = z
+    lr = torch.nn.functional.cosine_similarity(yr, zr, dim=1).mean()
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 2e-3
+    assert _cos(g_x, x.grad) > 0.995 and _cos(g_w, lin.weight.grad) > 0.995
+    assert _cos(g_b, lin.bias.grad) > 0.99 and _cos(g_g, bn.weight.grad) > 0.99
+    assert _rel(rm, bn.running_mean) < 2e-2 and _rel(rv, bn.running_var) < 2e-2
+
+
+def test_nn_bank_lookup_and_fifo(cuda_dev):
+    from declip_b200.model.nn_memory_bank import NNMemoryBankModule
+    from oracle import declip_ref, synth
+    bank0 = synth.synth_bank(512, 1024, seed=5)
+    m = NNMemoryBankModule(size=1024, topk=1)
+    m.load_bank(bank0, cuda_dev, ptr=1000)
+    ref = declip_ref.Bank(bank0, ptr=1000)
+    q = torch.nn.functional.normalize(torch.randn(40, 512), dim=1)
+    # make the queries near bank entries so the top-1 is unambiguous under bf16
+    q = torch.nn.functional.normalize(bank0.t()[torch.randint(0, 1024, (40,))] + 0.05 * q, dim=1)
+    for update in (False, True, True):
+        out = m(q.to(cuda_dev), update=update)[0]
+        want, idx = ref(q, update=update)
+        assert torch.equal(m.last_index.cpu().long(), idx)
+        assert torch.allclose(out.cpu(), want, atol=1e-6)
+    assert m.bank_ptr == ref.ptr                                 # wrap: tail written, pointer reset (memory_bank.py:81-84)
+    assert torch.allclose(m.bank.cpu(), ref.bank.t(), atol=1e-6)
+
+
+def test_mask_tokens_distribution():
+    from declip_b200.model.text_utils import MASK, mask_tokens_batch
+    from oracle import synth
+    ids = synth.synth_token_ids(512, seed=1)
+    g = torch.Generator().manual_seed(0)
+    mi, lab = mask_tokens_batch(ids, generator=g)
+    body = (ids != 0) & (ids != synth.SOT) & (ids != synth.EOT)
+    frac = (lab != -100).sum().item() / body.sum().item()
+    assert 0.13 < frac < 0.17
+    assert ((lab != -100) & ~body).sum().item() == 0              # never masks SOT / EOT / padding
+    m = lab != -100
+    assert 0.75 < (mi[m] == MASK).float().mean().item() < 0.85
+    assert torch.equal(mi[~m], ids[~m])
+
+
+def _build(case, dev):
+    from declip_b200.model import model_entry
+    from oracle import golden
+    c = case
+    cfg = dict(type='declip_vitb32', kwargs=dict(
+        image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]),
+        text_encode=dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=c["embed_dim"], transformer_layers=c["t_layers"]),
+        clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=c["embed_dim"],
+                  nn_size=c["nn_size"])))
+    model = model_entry(cfg)
+    sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(c)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    model.nn_replacer_text.load_bank(bank, dev)
+    batch = {"images": images.to(dev), "token_ids": mlm_ids.to(dev), "token_ids_aug": ids_aug.to(dev),
+             "mlm": (mlm_ids.to(dev), mlm_labels)}
+    return model, batch
+
+
+def _declip_loss(out, world=1):
+    """declip_solver.py:435-517 with the drop-in loss classes of this repo."""
+    from declip_b200.loss_functions import ClipInfoCELoss, NTXentLoss, SimsiamLoss
+    from oracle.declip_ref import LOSS_WEIGHTS as W
+    crit, ss, ntx = ClipInfoCELoss(), SimsiamLoss(), NTXentLoss(out["features"][0].shape[0])
+    li1, li2, lt1, lt2 = out["logits"]
+    li1a, li2a, lt1a, lt2a = out["logits_aug"]
+    clip = (crit(li1, lt1)[0] + crit(li2, lt2)[0] + crit(li1a, lt1a)[0] + crit(li2a, lt2a)[0]) / 4 / world
+    mlm = out["text_self_supervised"] / world
+    n1, n2, n1a, n2a = out["nn_text_logits"]
+    nn_ = (crit(n1, n1a)[0] + crit(n2, n2a)[0]) / 2 / world
+    p1, p2, z1, z2 = out["simsiam_features"]
+    sim = ss(p1, z1, p2, z2) / world
+    tf, f1, f2 = out["features"]
+    nt = (ntx(f1, tf) + ntx(f2, tf)) / world
+    loss = clip * W["clip_loss"] + sim * W["simsiam_loss"] + mlm * W["masking_language"] + nn_ * W["nn_text"]
+    return loss, dict(clip=clip, mlm=mlm, nn=nn_, simsiam=sim, nt_xent=nt)
+
+
+def test_declip_step_matches_reference_golden(cuda_dev):
+    from oracle import golden
+    g = golden.load("declip_vitb32_l2_b8")
+    model, batch = _build(g["case"], cuda_dev)
+    out = model(batch, return_dict=True)
+    loss, parts = _declip_loss(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    tol = dict(clip=2e-2, mlm=5e-2, nn=3e-2, simsiam=3e-3, nt_xent=3e-2)
+    msg = {k: (parts[k].item(), g["parts"][k]) for k in parts}
+    for k, v in g["parts"].items():
+        assert abs(parts[k].item() - v) <= tol[k], msg
+    assert abs(loss.item() - g["loss"]) <= 3e-2, (loss.item(), g["loss"])
+    for key in ("logits", "logits_aug", "nn_text_logits"):
+        for a, b in zip(out[key], g[key]):
+            assert _cos(a.cpu(), b) > 0.999, key
+    for a, b in zip(out["features"], g["features"]):
+        assert torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item() > 0.999
+    for a, b in zip(out["simsiam_features"], g["simsiam_features"]):
+        assert _cos(a.cpu(), b) > 0.995
+    params = dict(model.named_parameters())
+    assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
+    worst = []
+    for k, ref in g["grads"].items():
+        mine = params[k].grad.detach().float().reshape(-1).cpu()
+        cs = _cos(mine[golden.sample_index(mine.numel())], ref["sample"])
+        worst.append((cs, mine.norm().item() / (ref["norm"] + 1e-20), k))
+    worst.sort()
+    txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
+    assert worst[0][0] > 0.97, txt
+    assert all(0.85 < w[1] < 1.15 for w in worst), txt
+    # BatchNorm running statistics and the FIFO bank follow the reference
+    sd = model.state_dict()
+    for k, v in g["stats"].items():
+        assert _rel(sd[k].cpu(), v) < 3e-2, k
+    assert model.nn_replacer_text.bank_ptr == g["bank_ptr"]
+    tail = model.nn_replacer_text.bank[:2 * g["case"]["batch"]].t().cpu()
+    assert _cos(tail, g["bank_tail"]) > 0.999

@@ -60,3 +60,28 @@ def test_logit_scale_clamp_semantics():
     li.sum().backward()
     raw = ((i / i.norm(dim=-1, keepdim=True)) @ (t / (t.norm(dim=-1, keepdim=True) + 1e-10)).t()).sum()
     assert abs(ls.grad.item() - (torch.exp(torch.tensor(5.5)) * raw).item()) < 1e-2
+
+
+def test_declip_restatement_matches_reference_golden():
+    """oracle/declip_ref.py (DECLIP.forward + NN bank + SimSiam + MLM + the solver's loss composition) against the
+    golden vectors produced by the reference's own DECLIP module."""
+    from oracle import declip_ref
+    name = "declip_vitb32_l2_b8"
+    g = golden.load(name)
+    sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(g["case"])
+    res = declip_ref.declip_step(sd, images, mlm_ids, mlm_labels, ids_aug, bank)
+    assert abs(res["loss"].item() - g["loss"]) <= 5e-5
+    for k, v in g["parts"].items():
+        assert abs(res["parts"][k].item() - v) <= 1e-4, k
+    for key in ("logits", "logits_aug", "nn_text_logits", "simsiam_features", "features"):
+        for a, b in zip(res["out"][key], g[key]):
+            torch.testing.assert_close(a.detach(), b, rtol=3e-4, atol=1e-3)
+    assert set(res["grads"]) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        mine = res["grads"][k].reshape(-1)
+        samp = mine[golden.sample_index(mine.numel())]
+        assert (samp - ref["sample"]).norm().item() <= 3e-3 * (ref["sample"].norm().item() + 1e-9) + 1e-7, k
+    for k, v in g["stats"].items():                                   # BatchNorm running statistics
+        torch.testing.assert_close(res["stats"][k], v, rtol=1e-4, atol=1e-5)
+    assert res["bank_ptr"] == g["bank_ptr"]
+    assert abs(res["bank"].double().sum().item() - g["bank_checksum"]) < 1e-3   # FIFO enqueue of both text views

@@ -17,8 +17,31 @@ from oracle import golden, ref_harness, synth  # noqa: E402
 def main():
     torch.set_num_threads(os.cpu_count() or 8)
     os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
-    names = sys.argv[1:] or list(golden.CASES)
-    for name in names:
+    names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES))
+    for name in [n for n in names if n in golden.DECLIP_CASES]:
+        c = golden.DECLIP_CASES[name]
+        t0 = time.time()
+        sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(c)
+        res, model = ref_harness.reference_declip_step(sd, images, mlm_ids, mlm_labels, ids_aug, bank, c["embed_dim"],
+                                                       c["v_layers"], c["t_layers"])
+        o = res["out"]
+        blob = {
+            "case": c, "torch": torch.__version__,
+            "generator": "tools/make_golden.py via oracle/ref_harness.reference_declip_step (reference DECLIP, CPU fp32)",
+            "loss": res["loss"].item(), "parts": {k: v.item() for k, v in res["parts"].items()},
+            "logits": [t.detach().clone() for t in o["logits"]], "logits_aug": [t.detach().clone() for t in o["logits_aug"]],
+            "nn_text_logits": [t.detach().clone() for t in o["nn_text_logits"]],
+            "simsiam_features": [t.detach().clone() for t in o["simsiam_features"]],
+            "features": [t.detach().clone() for t in o["features"]],
+            "text_self_supervised": o["text_self_supervised"].item(),
+            "grads": golden.summarise_grads(res["grads"]), "stats": res["stats"],
+            "bank_ptr": res["bank_ptr"], "bank_checksum": res["bank"].double().sum().item(),
+            "bank_tail": res["bank"][:, :2 * c["batch"]].clone(),
+        }
+        torch.save(blob, golden.path(name))
+        print("%s: loss %.6f parts %s, %d grads, %.1fs -> %.1f KB" % (name, blob["loss"], {k: round(v, 4) for k, v in
+              blob["parts"].items()}, len(blob["grads"]), time.time() - t0, os.path.getsize(golden.path(name)) / 1024))
+    for name in [n for n in names if n in golden.CASES]:
         c = golden.CASES[name]
         t0 = time.time()
         sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"],
