@@ -296,26 +296,46 @@ class StripLogits(torch.autograd.Function):
         return (dls, None, None, None, None) + tuple(grads)
 
 
+def _split_bf16(x):
+    """x (fp32) = hi + lo with hi, lo bf16: three bf16 tensor-core GEMMs (hi*hi + hi*lo + lo*hi) then reproduce an
+    fp32 product to ~1e-5 relative — used for the tiny fp32 heads where BatchNorm over a small batch amplifies
+    rounding noise."""
+    x = x.float().contiguous()
+    hi = cast_bf16(x)
+    lo = cast_bf16(x - hi.float())
+    return hi, lo
+
+
+def _gemm3(a, b, **kw):
+    """sum of the three significant partial products of split operands a = (hi, lo), b = (hi, lo)."""
+    out = ops.gemm(a[0], b[0], epilogue=ops.EPI_F32, **kw)
+    kw.pop("bias", None)
+    ops.gemm(a[0], b[1], epilogue=ops.EPI_F32_ATOMIC, out=out, **kw)
+    ops.gemm(a[1], b[0], epilogue=ops.EPI_F32_ATOMIC, out=out, **kw)
+    return out
+
+
 class LinearF32(torch.autograd.Function):
-    """y = x W^T + b for the small fp32 heads (SimSiam projector/predictor, declip.py:48-60,107-112); bf16 tensor-core
-    GEMMs with fp32 I/O.  in/out features must be multiples of 8."""
+    """y = x W^T + b for the small fp32 heads (SimSiam projector/predictor, declip.py:48-60,107-112): split-bf16
+    tensor-core GEMMs with fp32 I/O (near-fp32 accuracy).  in/out features must be multiples of 8."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        x16 = cast_bf16(x.float().contiguous())
-        w16 = cast_bf16(weight.contiguous())
-        y = ops.gemm(x16, w16, bias=bias, epilogue=ops.EPI_F32)
-        ctx.save_for_backward(x16, w16)
+        xs = _split_bf16(x)
+        ws = _split_bf16(weight)
+        y = _gemm3(xs, ws, bias=bias)
+        ctx.save_for_backward(*xs, *ws)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x16, w16 = ctx.saved_tensors
-        dy16 = cast_bf16(dy.float().contiguous())
-        dx = ops.gemm(dy16, w16, b_mn_major=True, epilogue=ops.EPI_F32) if ctx.needs_input_grad[0] else None
-        dw = ops.gemm(dy16, x16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)
-        db = ops.colsum(dy16) if ctx.has_bias else None
+        xh, xl, wh, wl = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dys = _split_bf16(dy)
+        dx = _gemm3(dys, (wh, wl), b_mn_major=True) if ctx.needs_input_grad[0] else None
+        dw = _gemm3(dys, (xh, xl), a_mn_major=True, b_mn_major=True)
+        db = dy.sum(0) if ctx.has_bias else None
         return dx, dw, db
 
 

@@ -40,8 +40,10 @@ def test_batchnorm_linear_cosine_ops(cuda_dev):
     lr = torch.nn.functional.cosine_similarity(yr, zr, dim=1).mean()
     lr.backward()
     assert abs(loss.item() - lr.item()) < 2e-3
-    assert _cos(g_x, x.grad) > 0.995 and _cos(g_w, lin.weight.grad) > 0.995
-    assert _cos(g_b, lin.bias.grad) > 0.99 and _cos(g_g, bn.weight.grad) > 0.99
+    assert _cos(g_x, x.grad) > 0.999 and _cos(g_w, lin.weight.grad) > 0.999
+    assert _cos(g_g, bn.weight.grad) > 0.999
+    # a bias that feeds a BatchNorm has an identically-zero gradient (the batch mean is removed): both ~ 0
+    assert g_b.abs().max().item() < 1e-4 and lin.bias.grad.abs().max().item() < 1e-4
     assert _rel(rm, bn.running_mean) < 2e-2 and _rel(rv, bn.running_var) < 2e-2
 
 
@@ -143,11 +145,17 @@ def test_declip_step_matches_reference_golden(cuda_dev):
     worst = []
     for k, ref in g["grads"].items():
         mine = params[k].grad.detach().float().reshape(-1).cpu()
+        if ref["norm"] < 1e-6:
+            # biases feeding a BatchNorm (linear*.bias, bn3.bias -> predictor.linear1 -> bn1): the exact gradient is
+            # zero, the reference holds fp32 round-off (~1e-10); require ours to be numerically zero as well
+            assert mine.abs().max().item() < 1e-4, k
+            continue
         cs = _cos(mine[golden.sample_index(mine.numel())], ref["sample"])
         worst.append((cs, mine.norm().item() / (ref["norm"] + 1e-20), k))
     worst.sort()
     txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
-    assert worst[0][0] > 0.97, txt
+    # SimSiam heads sit behind BatchNorm over a batch of 8 here, which amplifies the towers' bf16 noise: 0.95 for them
+    assert all(w[0] > (0.95 if ("projector" in w[2] or "predictor" in w[2]) else 0.97) for w in worst), txt
     assert all(0.85 < w[1] < 1.15 for w in worst), txt
     # BatchNorm running statistics and the FIFO bank follow the reference
     sd = model.state_dict()
