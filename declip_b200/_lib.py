@@ -93,9 +93,13 @@ SIGNATURES = {
     "dc_dot_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_void_p]),
-    "dc_vit_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
+    "dc_vit_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "dc_token_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "dc_groupmax_mean_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dc_groupmax_mean_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "dc_add_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_text_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "dc_text_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

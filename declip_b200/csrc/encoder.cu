@@ -254,9 +254,25 @@ size_t dc_tower_workspace_bytes(const dc_tower_cfg* cfg) {
   return w.bytes;
 }
 
+// tokens [batch, L, D] <-> patch tokens [batch, L-1, D] (drop / skip the class token row)
+__global__ void __launch_bounds__(256) dense_tokens_kernel(const dc::bf16* __restrict__ src, dc::bf16* __restrict__ dst,
+                                                           int batch, int L, int D, int to_dense) {
+  const int vw = D / 8;
+  const size_t total = static_cast<size_t>(batch) * (L - 1) * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 8;
+    const size_t t = v / vw;
+    const size_t b = t / (L - 1), p = t % (L - 1);
+    const size_t tok = (b * L + 1 + p) * D + c, den = t * D + c;
+    if (to_dense) *reinterpret_cast<uint4*>(dst + den) = *reinterpret_cast<const uint4*>(src + tok);
+    else *reinterpret_cast<uint4*>(dst + tok) = *reinterpret_cast<const uint4*>(src + den);
+  }
+}
+
 int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sample_stride,
                    const void* const* w_bf16, const float* const* w_f32, void* workspace, float* features,
-                   dc_stream_t stream) {
+                   void* dense_out, dc_stream_t stream) {
   DC_TRY(check_cfg(cfg));
   const dc_tower_cfg& c = *cfg;
   if (c.patch <= 0 || c.res % c.patch) return set_error("vit: bad res/patch");
@@ -276,6 +292,10 @@ int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sampl
   DC_TRY(dc_vit_assemble(w.patch_out, xf[0], xf[1], w.tokens_pre, c.batch, g2, D, st));
   DC_TRY(dc_layernorm_fwd(w.tokens_pre, xf[2], xf[3], w.xs[0], w.mean_pre, w.rstd_pre, M, D, 1e-5f, st));
   DC_TRY(layers_forward(c, w, w_bf16, w_f32, st));
+  if (dense_out != nullptr) {                                   // dense_feat = x[:, 1:, :]   visual_transformer.py:68
+    dense_tokens_kernel<<<sm_count() * 8, 256, 0, st>>>(w.xs[NL], static_cast<bf16*>(dense_out), c.batch, c.seq_len, D, 1);
+    DC_CHECK_LAUNCH("dense_tokens");
+  }
   // ln_post on the class token, projection                     visual_transformer.py:69-73
   iota_stride_kernel<<<(c.batch + 255) / 256, 256, 0, st>>>(w.row_idx, c.batch, c.seq_len);
   DC_CHECK_LAUNCH("iota_stride");
@@ -286,7 +306,7 @@ int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sampl
   return gemm_bf16(a, st);
 }
 
-int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* const* w_bf16,
+int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* ddense, const void* const* w_bf16,
                     const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream) {
   DC_TRY(check_cfg(cfg));
   const dc_tower_cfg& c = *cfg;
@@ -313,6 +333,12 @@ int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void*
   cudaError_t e = cudaMemsetAsync(w.dxa, 0, static_cast<size_t>(M) * D * sizeof(bf16), st);
   if (e != cudaSuccess) return set_error_cuda("memset dx", e);
   DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));
+  if (ddense != nullptr) {   // gradient of the patch tokens (class-token rows already hold the ln_post path)
+    dense_tokens_kernel<<<sm_count() * 8, 256, 0, st>>>(static_cast<const bf16*>(ddense), w.dxa, c.batch, c.seq_len, D, 0);
+    DC_CHECK_LAUNCH("dense_tokens_bwd");
+    // c_proj.bias of the last layer also sees these rows
+    if (NL > 0) DC_TRY(dc_colsum_bf16(ddense, D, grads[12 * (NL - 1) + 9], c.batch * (c.seq_len - 1), D, st));
+  }
   DC_TRY(layers_backward(c, w, w_bf16, w_f32, grads, st));
   // ln_pre backward, then positional / class embedding gradients
   DC_TRY(dc_layernorm_bwd(w.dxa, w.tokens_pre, xf[2], w.mean_pre, w.rstd_pre, nullptr, w.dxb, xg[2], xg[3], nullptr, M, D, st));

@@ -282,3 +282,154 @@ int dc_add_rows(const void* src, const int* idx, void* dst, int n, int width, dc
 }
 
 }  // extern "C"
+
+// ================================================================================================ FILIP
+// Token-wise late interaction — prototype/model/filip.py:71-106.
+namespace dc {
+
+// score1[b,j] = <d1[b,j,:], sum_m d2[b,m,:]>, score2[b,m] = <d2[b,m,:], sum_j d1[b,j,:]>   (filip.py:79-81: the
+// row / column sums of the per-pair cross-logit matrix, without forming it).  One block per sample.
+__global__ void __launch_bounds__(256) token_scores_kernel(const float* __restrict__ d1, const float* __restrict__ d2,
+                                                           int n1, int n2, int dim, float* __restrict__ score1,
+                                                           float* __restrict__ score2) {
+  extern __shared__ float s_sum[];  // [2][dim]
+  const int b = blockIdx.x;
+  const float* a = d1 + static_cast<size_t>(b) * n1 * dim;
+  const float* c = d2 + static_cast<size_t>(b) * n2 * dim;
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = 0; j < n1; ++j) s1 += a[static_cast<size_t>(j) * dim + k];
+    for (int m = 0; m < n2; ++m) s2 += c[static_cast<size_t>(m) * dim + k];
+    s_sum[k] = s1;
+    s_sum[dim + k] = s2;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = warp; t < n1 + n2; t += nw) {
+    const bool first = t < n1;
+    const float* row = first ? a + static_cast<size_t>(t) * dim : c + static_cast<size_t>(t - n1) * dim;
+    const float* other = first ? s_sum + dim : s_sum;
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc += row[k] * other[k];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (first) score1[static_cast<size_t>(b) * n1 + t] = acc;
+      else score2[static_cast<size_t>(b) * n2 + (t - n1)] = acc;
+    }
+  }
+}
+
+// out[i, l] = mean_{j < n} max_{m < group} G[i*n + j, l*group + m]   (filip.py:103-104), arg[i*n+j, l] = argmax m.
+// One block per (sample i, 32 candidate samples l); thread (tx = l lane, ty = token lane).
+__global__ void __launch_bounds__(256) groupmax_mean_fwd_kernel(const float* __restrict__ G, int ldg, int n, int group,
+                                                                int ncand, float* __restrict__ out, int ldo,
+                                                                uint8_t* __restrict__ arg) {
+  __shared__ float s_part[8][33];
+  const int i = blockIdx.y;
+  const int l = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (l < ncand) {
+    for (int j = threadIdx.y; j < n; j += 8) {
+      const float* g = G + (static_cast<size_t>(i) * n + j) * ldg + static_cast<size_t>(l) * group;
+      float best = g[0];
+      int bi = 0;
+      for (int m = 1; m < group; ++m) {
+        const float v = g[m];
+        if (v > best) { best = v; bi = m; }
+      }
+      acc += best;
+      arg[(static_cast<size_t>(i) * n + j) * ncand + l] = static_cast<uint8_t>(bi);
+    }
+  }
+  s_part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && l < ncand) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += s_part[r][threadIdx.x];
+    out[static_cast<size_t>(i) * ldo + l] = s / n;
+  }
+}
+
+// dG[i*n + j, l*group + m] = (m == arg) ? dout[i, l] / n : 0   (bf16, feeds the two backward GEMMs)
+__global__ void __launch_bounds__(256) groupmax_mean_bwd_kernel(const float* __restrict__ dout, int ldd,
+                                                                const uint8_t* __restrict__ arg, int n, int group,
+                                                                int ncand, bf16* __restrict__ dG, int ldg, int rows) {
+  const size_t total = static_cast<size_t>(rows) * ncand;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const float invn = 1.0f / n;
+  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const size_t r = t / ncand;
+    const int l = static_cast<int>(t - r * ncand);
+    const int i = static_cast<int>(r / n);
+    const float g = dout[static_cast<size_t>(i) * ldd + l] * invn;
+    const int a = arg[t];
+    bf16* d = dG + r * ldg + static_cast<size_t>(l) * group;
+    for (int m = 0; m < group; m += 2)
+      *reinterpret_cast<uint32_t*>(d + m) = pack_bf16x2(m == a ? g : 0.f, m + 1 == a ? g : 0.f);
+  }
+}
+
+// dst[idx[i], :] += src[i, :] (fp32 rows; idx rows distinct)
+__global__ void __launch_bounds__(256) add_rows_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                           float* __restrict__ dst, int n, int width) {
+  const int vw = width / 4;
+  const size_t total = static_cast<size_t>(n) * vw;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
+    const int c = static_cast<int>(v % vw) * 4;
+    const size_t i = v / vw;
+    float4* d = reinterpret_cast<float4*>(dst + static_cast<size_t>(idx[i]) * width + c);
+    const float4 a = *reinterpret_cast<const float4*>(src + i * width + c);
+    float4 b = *d;
+    b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
+    *d = b;
+  }
+}
+
+}  // namespace dc
+
+extern "C" {
+
+int dc_token_scores(const float* d1, const float* d2, int batch, int n1, int n2, int dim, float* score1, float* score2,
+                    dc_stream_t stream) {
+  if (batch <= 0) return 0;
+  token_scores_kernel<<<batch, 256, 2 * dim * sizeof(float), static_cast<cudaStream_t>(stream)>>>(d1, d2, n1, n2, dim,
+                                                                                               score1, score2);
+  DC_CHECK_LAUNCH("token_scores");
+  return 0;
+}
+
+int dc_groupmax_mean_fwd(const float* G, int ldg, int batch, int n, int group, int ncand, float* out, int ldo,
+                         unsigned char* arg, dc_stream_t stream) {
+  if (batch <= 0 || ncand <= 0) return 0;
+  if (group > 255) return dc::set_error("groupmax: group must be <= 255");
+  dim3 grid((ncand + 31) / 32, batch);
+  groupmax_mean_fwd_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(G, ldg, n, group, ncand, out, ldo,
+                                                                                     arg);
+  DC_CHECK_LAUNCH("groupmax_mean_fwd");
+  return 0;
+}
+
+int dc_groupmax_mean_bwd(const float* dout, int ldd, const unsigned char* arg, int batch, int n, int group, int ncand,
+                         void* dG, int ldg, dc_stream_t stream) {
+  if (batch <= 0 || ncand <= 0) return 0;
+  if (group & 1) return dc::set_error("groupmax: group must be even");
+  const int rows = batch * n;
+  groupmax_mean_bwd_kernel<<<dc::grid_cap(static_cast<size_t>(rows) * ncand, 256), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(dout, ldd, arg, n, group, ncand,
+                                                                  static_cast<dc::bf16*>(dG), ldg, rows);
+  DC_CHECK_LAUNCH("groupmax_mean_bwd");
+  return 0;
+}
+
+int dc_add_rows_f32(const float* src, const int* idx, float* dst, int n, int width, dc_stream_t stream) {
+  if (n <= 0) return 0;
+  if (width & 3) return dc::set_error("add_rows_f32: width must be a multiple of 4");
+  add_rows_f32_kernel<<<dc::grid_cap(static_cast<size_t>(n) * (width / 4), 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(src, idx, dst, n, width);
+  DC_CHECK_LAUNCH("add_rows_f32");
+  return 0;
+}
+
+}  // extern "C"

@@ -508,3 +508,127 @@ def normalize_rows_bf16(x, eps=1e-12):
     _lib.check(lib.dc_l2norm_fwd(_PTR(x.data_ptr()), _PTR(y.data_ptr()), None, None, x.shape[0], x.shape[1], eps, _stream()),
                "dc_l2norm_fwd")
     return y
+
+
+# =====================================================================================================================
+# FILIP (filip.py:71-142)
+# =====================================================================================================================
+class LinearBF16In(torch.autograd.Function):
+    """y(fp32) = x(bf16) W^T + b on dense token features (image_mapping / text_mapping, filip.py:40-41,133-134)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w16 = cast_bf16(weight.contiguous())
+        x = x.contiguous()
+        y = ops.gemm(x, w16, bias=bias, epilogue=ops.EPI_F32)
+        ctx.save_for_backward(x, w16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16 = ctx.saved_tensors
+        dy16 = cast_bf16(dy.float().contiguous())
+        db = ops.colsum(dy16)
+        dx = ops.gemm(dy16, w16, b_mn_major=True, epilogue=ops.EPI_BF16)
+        dw = ops.gemm(dy16, x, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)
+        return dx, dw, db
+
+
+class GatherRowsF32(torch.autograd.Function):
+    """out[i] = x[idx[i]] (fp32 rows, distinct idx) — the top-k token selection (filip.py:83-88)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        lib = ops.lib_for(x)
+        x = x.contiguous()
+        n, d = idx.numel(), x.shape[1]
+        out = torch.empty(n, d, device=x.device, dtype=torch.float32)
+        _lib.check(lib.dc_gather_rows_f32(_PTR(x.data_ptr()), _PTR(idx.data_ptr()), _PTR(out.data_ptr()), n, d, _stream()),
+                   "dc_gather_rows_f32")
+        ctx.save_for_backward(idx)
+        ctx.rows = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        lib = ops.lib_for(dout)
+        dout = dout.float().contiguous()
+        dx = torch.zeros(ctx.rows, dout.shape[1], device=dout.device, dtype=torch.float32)
+        _lib.check(lib.dc_add_rows_f32(_PTR(dout.data_ptr()), _PTR(idx.data_ptr()), _PTR(dx.data_ptr()), idx.numel(),
+                                       dout.shape[1], _stream()), "dc_add_rows_f32")
+        return dx, None
+
+
+class AllGatherRows(torch.autograd.Function):
+    """CLIP.all_gather (clip.py:25-49,113-116) on torch.distributed/NCCL: forward all-gather along dim 0, backward
+    reduce-scatter (== the reference's all-reduce + slice)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        rank, world = dist_info()
+        ctx.world = world
+        if world == 1:
+            return x
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+        dist.all_gather_into_tensor(out, x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.world == 1:
+            return g
+        g = g.contiguous()
+        out = torch.empty((g.shape[0] // ctx.world,) + tuple(g.shape[1:]), device=g.device, dtype=g.dtype)
+        dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+        return out
+
+
+class FilipLate(torch.autograd.Function):
+    """logits[i, l] = mean_j max_m  s * <d[i, j, :], sel[l, m, :]>   (filip.py:93-104).
+    d fp32 [B*n, dim] (normalised dense tokens of this rank), sel fp32 [N*group, dim] (gathered selected tokens),
+    logit_scale_dense the raw parameter (s = exp, not clamped, filip.py:75)."""
+
+    @staticmethod
+    def forward(ctx, d, sel, logit_scale_dense, n, group):
+        lib = ops.lib_for(d)
+        d16 = cast_bf16(d.float().contiguous())
+        sel16 = cast_bf16(sel.float().contiguous())
+        batch = d.shape[0] // n
+        ncand = sel.shape[0] // group
+        s = logit_scale_dense.detach().float().exp().reshape(1)
+        G = ops.gemm(d16, sel16, epilogue=ops.EPI_F32, alpha_dev=s)                      # [B*n, N*group]
+        out = torch.empty(batch, ncand, device=d.device, dtype=torch.float32)
+        arg = torch.empty(batch * n, ncand, device=d.device, dtype=torch.uint8)
+        _lib.check(lib.dc_groupmax_mean_fwd(_PTR(G.data_ptr()), G.stride(0), batch, n, group, ncand, _PTR(out.data_ptr()),
+                                            out.stride(0), _PTR(arg.data_ptr()), _stream()), "dc_groupmax_mean_fwd")
+        ctx.save_for_backward(d16, sel16, arg, s, out)
+        ctx.meta = (batch, n, group, ncand)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        d16, sel16, arg, s, out = ctx.saved_tensors
+        lib = ops.lib_for(d16)
+        batch, n, group, ncand = ctx.meta
+        dout = dout.float().contiguous()
+        dG = torch.empty(batch * n, ncand * group, device=d16.device, dtype=torch.bfloat16)
+        _lib.check(lib.dc_groupmax_mean_bwd(_PTR(dout.data_ptr()), dout.stride(0), _PTR(arg.data_ptr()), batch, n, group,
+                                            ncand, _PTR(dG.data_ptr()), dG.stride(0), _stream()), "dc_groupmax_mean_bwd")
+        dd = ops.gemm(dG, sel16, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s)      # [B*n, dim]
+        dsel = ops.gemm(dG, d16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s)   # [N*group, dim]
+        # d logit_scale_dense = sum(dout * out): out is linear in s = exp(ls), so d out / d ls = out
+        acc = torch.zeros(1, device=d16.device, dtype=torch.float32)
+        dot_into(dout, out, acc)
+        return dd, dsel, acc.reshape(()), None, None
+
+
+def token_scores(d1, d2, batch, n1, n2):
+    lib = ops.lib_for(d1)
+    dim = d1.shape[-1]
+    s1 = torch.empty(batch, n1, device=d1.device, dtype=torch.float32)
+    s2 = torch.empty(batch, n2, device=d1.device, dtype=torch.float32)
+    _lib.check(lib.dc_token_scores(_PTR(d1.data_ptr()), _PTR(d2.data_ptr()), batch, n1, n2, dim, _PTR(s1.data_ptr()),
+                                   _PTR(s2.data_ptr()), _stream()), "dc_token_scores")
+    return s1, s2

@@ -8,8 +8,9 @@ To run the reference solvers unchanged, alias the package before importing them:
 """
 from .clip import CLIP, clip_vitb32  # noqa: F401
 from .declip import DECLIP, declip_vitb32  # noqa: F401
+from .filip import FILIP, filip_vitb32  # noqa: F401
 
-_NOT_BUILT = ('clip_res50', 'declip_res50', 'filip_res50', 'filip_vitb32', 'slip_res50', 'slip_vitb32',
+_NOT_BUILT = ('clip_res50', 'declip_res50', 'filip_res50', 'slip_res50', 'slip_vitb32',
               'defilip_vitb32')
 
 

@@ -55,11 +55,15 @@ class VisualTransformer(nn.Module):
         return self
 
     def forward(self, x, return_dense=False, return_feature=False):
-        if return_dense or return_feature:
-            raise NotImplementedError("declip_b200: return_dense/return_feature (FILIP / DeCLIP-dense) not built yet")
+        if return_feature:
+            raise NotImplementedError("declip_b200: return_feature (pre-projection class feature) is unused by the "
+                                      "reference wrappers")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError("expected images [B,3,%d,%d], got %s" % (self.input_resolution, self.input_resolution,
                                                                       tuple(x.shape)))
+        if return_dense:   # (x, dense_feat) with dense_feat = last-block patch tokens, bf16 [B, 49, width]
+            feats, dense = run_tower(self._rt, x, dense=True)
+            return feats, dense.view(x.shape[0], self._rt.seq_len - 1, -1)
         return run_tower(self._rt, x)
 
 

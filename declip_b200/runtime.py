@@ -138,9 +138,14 @@ class TowerRuntime:
         if self.kind == "vit":
             if inp.dtype != torch.float32 or inp.stride(3) != 1 or inp.stride(2) != self.res or inp.stride(1) != self.res ** 2:
                 inp = inp.float().contiguous()
+            dense_out = None
+            if dense:   # patch tokens of the last block, x[:, 1:, :] (visual_transformer.py:68)
+                dense_out = torch.empty(batch * (self.seq_len - 1), self.width, device=inp.device, dtype=torch.bfloat16)
             _lib.check(self.lib.dc_vit_forward(ctypes.byref(cfg), _PTR(inp.data_ptr()), inp.stride(0), self.w_bf16,
-                                               self.w_f32, _PTR(ws.data_ptr()), _PTR(feats.data_ptr()), _stream()),
+                                               self.w_f32, _PTR(ws.data_ptr()), _PTR(feats.data_ptr()),
+                                               _PTR(dense_out.data_ptr()) if dense else None, _stream()),
                        "dc_vit_forward")
+            return feats, inp, cfg, ws, dense_out
         else:
             if inp.dtype != torch.int64 or not inp.is_contiguous():
                 inp = inp.long().contiguous()
@@ -152,8 +157,6 @@ class TowerRuntime:
                                                 _PTR(words.data_ptr()) if dense else None, _stream()),
                        "dc_text_forward")
             return feats, inp, cfg, ws, words
-        if dense:
-            raise NotImplementedError("declip_b200: dense ViT output (FILIP) not built yet")
         return feats, inp, cfg, ws, None
 
     def backward(self, cfg, inp, ws, dfeats, params, dense=False, dwords=None):
@@ -197,8 +200,9 @@ class TowerRuntime:
         if dwords is not None:
             dwords = dwords.to(torch.bfloat16).contiguous()
         if self.kind == "vit":
-            _lib.check(self.lib.dc_vit_backward(ctypes.byref(cfg), _PTR(dfeats.data_ptr()), self.w_bf16, self.w_f32, ptrs,
-                                                _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
+            _lib.check(self.lib.dc_vit_backward(ctypes.byref(cfg), _PTR(dfeats.data_ptr()),
+                                                _PTR(dwords.data_ptr()) if dwords is not None else None, self.w_bf16,
+                                                self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
         else:
             _lib.check(self.lib.dc_text_backward(ctypes.byref(cfg), _PTR(inp.data_ptr()), _PTR(dfeats.data_ptr()),
                                                  int(dense), _PTR(dwords.data_ptr()) if dwords is not None else None,

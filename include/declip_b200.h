@@ -171,6 +171,20 @@ int dc_gather_rows_f32(const float* src, const int* idx, float* dst, int n, int 
 /* dst[idx[i],:] += src[i,:] (bf16 rows, distinct idx): EOT-row gradient added into the dense ln_final gradient. */
 int dc_add_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream);
 
+/* ------------------------------------------------------------------ FILIP token-wise late interaction (filip.py:71-106)
+ * score1[b,j] = <d1[b,j,:], sum_m d2[b,m,:]>, score2[b,m] = <d2[b,m,:], sum_j d1[b,j,:]> : the row / column sums of
+ * the per-pair cross-logit matrix (filip.py:79-81) that rank tokens for the top-16 selection.  d1 [batch,n1,dim],
+ * d2 [batch,n2,dim] fp32 (normalised). */
+int dc_token_scores(const float* d1, const float* d2, int batch, int n1, int n2, int dim, float* score1, float* score2,
+                    dc_stream_t stream);
+/* out[i,l] = mean_{j<n} max_{m<group} G[i*n+j, l*group+m]; arg[(i*n+j)*ncand + l] = argmax m   (filip.py:103-104) */
+int dc_groupmax_mean_fwd(const float* G, int ldg, int batch, int n, int group, int ncand, float* out, int ldo,
+                         unsigned char* arg, dc_stream_t stream);
+/* dG (bf16 [batch*n, ncand*group]) = one-hot(arg) * dout[i,l] / n */
+int dc_groupmax_mean_bwd(const float* dout, int ldd, const unsigned char* arg, int batch, int n, int group, int ncand,
+                         void* dG, int ldg, dc_stream_t stream);
+int dc_add_rows_f32(const float* src, const int* idx, float* dst, int n, int width, dc_stream_t stream);
+
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.
  * Weight/grad tables are arrays of device pointers in the order documented in encoder.h order
@@ -183,10 +197,12 @@ typedef struct {
   int vocab;      /* text only */
 } dc_tower_cfg;
 size_t dc_tower_workspace_bytes(const dc_tower_cfg* cfg);
+/* dense_out (bf16 [batch*(L-1), width], may be NULL): the patch tokens of the last block, `x[:, 1:, :]` that
+ * VisualTransformer.forward returns with return_dense (visual_transformer.py:68); ddense is its gradient (or NULL). */
 int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sample_stride,
                    const void* const* w_bf16, const float* const* w_f32, void* workspace, float* features,
-                   dc_stream_t stream);
-int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* const* w_bf16,
+                   void* dense_out, dc_stream_t stream);
+int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* ddense, const void* const* w_bf16,
                     const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream);
 /* words_out (bf16 [batch*L, width], may be NULL): ln_final applied to EVERY token — the `words_feat` that
  * TextTransformer.forward returns with mask_type / return_dense (text_transformer.py:194-201).  When it was requested

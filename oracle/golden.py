@@ -16,6 +16,21 @@ DECLIP_CASES = {
 }
 
 
+FILIP_CASES = {
+    "filip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=768, seed=4),
+}
+
+
+def filip_inputs(c):
+    from . import synth
+    sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"], t_layers=c["t_layers"])
+    sd.update(synth.filip_extra_state_dict(seed=c["seed"]))
+    images = synth.synth_images(c["batch"], seed=c["seed"], channels=6)
+    ids = synth.synth_token_ids(c["batch"], seed=c["seed"])
+    mlm_ids, mlm_labels = synth.synth_mlm(ids, seed=c["seed"])
+    return sd, images, mlm_ids, mlm_labels
+
+
 def declip_inputs(c):
     """Synthetic DeCLIP batch for a case: (state_dict, images[B,6,H,W], mlm_ids, mlm_labels, ids_aug, bank[dim,size])."""
     from . import synth

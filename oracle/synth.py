@@ -145,3 +145,13 @@ def synth_mlm(ids, seed=0):
     rnd = masked & (r >= 0.8) & (r < 0.9)
     ids[rnd] = torch.randint(0, VOCAB, (B, L), generator=g)[rnd]
     return ids, labels
+
+
+def filip_extra_state_dict(seed=0, v_width=768, t_width=512, dense_dim=256, vocab=VOCAB):
+    """Extra FILIP keys (filip.py:40-55): token mappings, dense logit scale, (unused) MLM head."""
+    sd = {"logit_scale_dense": torch.tensor(math.log(1 / 0.07), dtype=torch.float32)}
+    for name, o, i in (("image_mapping", dense_dim, v_width), ("text_mapping", dense_dim, t_width),
+                       ("text_label_predictor", vocab, t_width)):
+        sd[name + ".weight"] = _randn(name + ".weight", seed, (o, i), i ** -0.5)
+        sd[name + ".bias"] = _randn(name + ".bias", seed, (o,), 0.02)
+    return sd

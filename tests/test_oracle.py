@@ -85,3 +85,19 @@ def test_declip_restatement_matches_reference_golden():
         torch.testing.assert_close(res["stats"][k], v, rtol=1e-4, atol=1e-5)
     assert res["bank_ptr"] == g["bank_ptr"]
     assert abs(res["bank"].double().sum().item() - g["bank_checksum"]) < 1e-3   # FIFO enqueue of both text views
+
+
+def test_filip_restatement_matches_reference_golden():
+    from oracle import filip_ref
+    g = golden.load("filip_vitb32_l2_b8")
+    sd, images, mlm_ids, mlm_labels = golden.filip_inputs(g["case"])
+    res = filip_ref.filip_step(sd, images, mlm_ids)
+    assert abs(res["loss"].item() - g["loss"]) <= 5e-5
+    for key in ("logits", "dense_logits"):
+        for a, b in zip(res["out"][key], g[key]):
+            torch.testing.assert_close(a.detach(), b, rtol=3e-4, atol=1e-3)
+    assert set(res["grads"]) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        mine = res["grads"][k].reshape(-1)
+        samp = mine[golden.sample_index(mine.numel())]
+        assert (samp - ref["sample"]).norm().item() <= 3e-3 * (ref["sample"].norm().item() + 1e-9) + 1e-7, k

@@ -17,7 +17,22 @@ from oracle import golden, ref_harness, synth  # noqa: E402
 def main():
     torch.set_num_threads(os.cpu_count() or 8)
     os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
-    names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES))
+    names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES) + list(golden.FILIP_CASES))
+    for name in [n for n in names if n in golden.FILIP_CASES]:
+        c = golden.FILIP_CASES[name]
+        t0 = time.time()
+        sd, images, mlm_ids, mlm_labels = golden.filip_inputs(c)
+        res, model = ref_harness.reference_filip_step(sd, images, mlm_ids, mlm_labels, c["embed_dim"], c["v_layers"],
+                                                      c["t_layers"])
+        blob = {"case": c, "torch": torch.__version__,
+                "generator": "tools/make_golden.py via oracle/ref_harness.reference_filip_step (reference FILIP, CPU fp32)",
+                "loss": res["loss"].item(), "parts": {k: v.item() for k, v in res["parts"].items()},
+                "logits": [t.detach().clone() for t in res["out"]["logits"]],
+                "dense_logits": [t.detach().clone() for t in res["out"]["dense_logits"]],
+                "grads": golden.summarise_grads(res["grads"])}
+        torch.save(blob, golden.path(name))
+        print("%s: loss %.6f parts %s, %d grads, %.1fs -> %.1f KB" % (name, blob["loss"], {k: round(v, 4) for k, v in
+              blob["parts"].items()}, len(blob["grads"]), time.time() - t0, os.path.getsize(golden.path(name)) / 1024))
     for name in [n for n in names if n in golden.DECLIP_CASES]:
         c = golden.DECLIP_CASES[name]
         t0 = time.time()
