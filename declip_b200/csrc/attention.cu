@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(LP * 2) attn_fwd_kernel(const bf16* __restrict
   const int m0 = warp * 16;
   if (m0 >= L) return;  // whole warp is padding
 
+  // causal: key tiles entirely above the diagonal of this warp's 16 query rows are fully masked -> skipped
+  const int nt_lim = causal ? min(NT, (m0 + 16) / 8) : NT;   // key n-tiles that can be unmasked
+  const int kt_lim = (nt_lim + 1) / 2;                        // key k-steps (16 keys) for P V
   float s[NT][4];
 #pragma unroll
   for (int n = 0; n < NT; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
@@ -98,10 +101,12 @@ __global__ void __launch_bounds__(LP * 2) attn_fwd_kernel(const bf16* __restrict
     load_a(sQ, HS, m0, k * 16, a);
 #pragma unroll
     for (int n = 0; n < NT; n += 2) {
-      uint32_t bb[4];
-      load_b_nk(sK, HS, n * 8, k * 16, bb);
-      mma_bf16(s[n], a, bb[0], bb[1]);
-      mma_bf16(s[n + 1], a, bb[2], bb[3]);
+      if (n < nt_lim) {
+        uint32_t bb[4];
+        load_b_nk(sK, HS, n * 8, k * 16, bb);
+        mma_bf16(s[n], a, bb[0], bb[1]);
+        mma_bf16(s[n + 1], a, bb[2], bb[3]);
+      }
     }
   }
   // masked softmax over keys; rows r0 = m0+g, r1 = m0+g+8
@@ -154,6 +159,7 @@ __global__ void __launch_bounds__(LP * 2) attn_fwd_kernel(const bf16* __restrict
   for (int n = 0; n < HD / 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
+    if (k >= kt_lim) continue;   // P is exactly zero there
     uint32_t a[4];
     a[0] = pack_bf16x2(s[2 * k][0] * inv0, s[2 * k][1] * inv0);
     a[1] = pack_bf16x2(s[2 * k][2] * inv1, s[2 * k][3] * inv1);
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
       s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
       dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
     }
+    const int nt_lim = causal ? min(NT, (m0 + 16) / 8) : NT;   // fully-masked key tiles are skipped (P = dS = 0)
 #pragma unroll
     for (int k = 0; k < HD / 16; ++k) {
       uint32_t aq[4], ad[4];
@@ -253,13 +260,15 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
       load_a(sdO, HS, m0, k * 16, ad);
 #pragma unroll
       for (int n = 0; n < NT; n += 2) {
-        uint32_t bk[4], bv[4];
-        load_b_nk(sK, HS, n * 8, k * 16, bk);
-        load_b_nk(sV, HS, n * 8, k * 16, bv);
-        mma_bf16(s[n], aq, bk[0], bk[1]);
-        mma_bf16(s[n + 1], aq, bk[2], bk[3]);
-        mma_bf16(dp[n], ad, bv[0], bv[1]);
-        mma_bf16(dp[n + 1], ad, bv[2], bv[3]);
+        if (n < nt_lim) {
+          uint32_t bk[4], bv[4];
+          load_b_nk(sK, HS, n * 8, k * 16, bk);
+          load_b_nk(sV, HS, n * 8, k * 16, bv);
+          mma_bf16(s[n], aq, bk[0], bk[1]);
+          mma_bf16(s[n + 1], aq, bk[2], bk[3]);
+          mma_bf16(dp[n], ad, bv[0], bv[1]);
+          mma_bf16(dp[n + 1], ad, bv[2], bv[3]);
+        }
       }
     }
     const float* l = lse + (static_cast<size_t>(b) * heads + h) * L;
@@ -314,10 +323,12 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
         }
       }
     };
-    // dQ[q][d] = sum_key dS[q][key] K[key][d]
+    const int w16 = m0 / 16;
+    // dQ[q][d] = sum_key dS[q][key] K[key][d]          (causal: keys beyond this query tile contribute zero)
     zero_acc();
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
+      if (causal && k > w16) continue;
       uint32_t a[4];
       load_a(sdS, PS, m0, k * 16, a);
 #pragma unroll
@@ -333,6 +344,7 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
     zero_acc();
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
+      if (causal && k < w16) continue;                  // queries before this key tile never attend to it
       uint32_t a[4];
       load_a_t(sdS, PS, m0, k * 16, a);
 #pragma unroll
@@ -348,6 +360,7 @@ __global__ void __launch_bounds__(LP * 2) attn_bwd_kernel(const bf16* __restrict
     zero_acc();
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
+      if (causal && k < w16) continue;
       uint32_t a[4];
       load_a_t(sP, PS, m0, k * 16, a);
 #pragma unroll

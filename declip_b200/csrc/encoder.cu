@@ -406,7 +406,7 @@ int dc_text_backward(const dc_tower_cfg* cfg, const long long* ids, const float*
     DC_TRY(dc_scatter_rows(w.drow2, w.row_idx, w.dxa, c.batch, D, st));
   }
   DC_TRY(layers_backward(c, w, w_bf16, w_f32, grads, st));
-  return dc_text_embed_bwd(ids, w.dxa, xg[0], xg[1], c.batch, c.seq_len, D, st);
+  return dc_text_embed_bwd(ids, w.dxa, xg[0], xg[1], dense ? nullptr : w.row_idx, c.batch, c.seq_len, D, st);
 }
 
 }  // extern "C"

@@ -362,15 +362,20 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const long long* __rest
 }
 
 // Embedding backward: scatter-add into the dense fp32 table gradient with vector reductions.
+// `last_row` (may be NULL): per-sample row index of the EOT token; rows after it carry an exactly-zero gradient
+// (causal attention, nothing downstream reads them) and are skipped — this also removes the atomic pile-up of all
+// padding positions on embedding row 0.
 __global__ void __launch_bounds__(256) text_embed_bwd_kernel(const long long* __restrict__ ids,
                                                              const bf16* __restrict__ dx, float* __restrict__ dtable,
-                                                             int batch, int L, int width) {
+                                                             const int* __restrict__ last_row, int batch, int L,
+                                                             int width) {
   const int vw = width / 8;
   const size_t total = static_cast<size_t>(batch) * L * vw;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total; v += stride) {
     const int c = static_cast<int>(v % vw) * 8;
     const size_t tok = v / vw;
+    if (last_row != nullptr && static_cast<int>(tok) > last_row[tok / L]) continue;
     const long long id = ids[tok];
     const uint4 u = *reinterpret_cast<const uint4*>(dx + tok * width + c);
     const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
@@ -673,12 +678,12 @@ int dc_text_embed(const long long* ids, const float* table, const float* pos, vo
   return 0;
 }
 
-int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, int batch, int L, int width,
-                      dc_stream_t stream) {
+int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, const int* last_row, int batch,
+                      int L, int width, dc_stream_t stream) {
   const size_t total = static_cast<size_t>(batch) * L * (width / 8);
   if (dtable != nullptr) {
     text_embed_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ids, static_cast<const bf16*>(dx), dtable, batch, L, width);
+        ids, static_cast<const bf16*>(dx), dtable, last_row, batch, L, width);
     DC_CHECK_LAUNCH("text_embed_bwd");
   }
   if (dpos != nullptr) return dc_colsum_bf16(dx, L * width, dpos, batch, L * width, stream);

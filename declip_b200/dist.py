@@ -25,11 +25,40 @@ def barrier():
 
 
 class DistModule(Module):
-    def __init__(self, module, sync=False):
+    def __init__(self, module, sync=False, overlap=True):
         super().__init__()
         self.module = module
         self.sync = sync
+        self._pending = {}        # id(rt) -> (rt, side-stream event) of all-reduces launched during backward
+        self._side = None
         self.broadcast_params()
+        if overlap and get_world_size() > 1:
+            for rt in self._runtimes():
+                rt.grad_ready_hook = self._on_tower_grads_ready
+
+    def _on_tower_grads_ready(self, rt):
+        """Called from the tower's backward as soon as its last kernel is enqueued: all-reduce the tower's flat
+        gradient buffer on a side stream, overlapping the backward of the other tower (the reference overlaps per
+        parameter through grad-accumulator hooks, dist.py:63-74)."""
+        if rt.grad_flat is None or not self._aliased(rt):
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            dist.all_reduce(rt.grad_flat)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._pending[id(rt)] = (rt, done)
+
+    @staticmethod
+    def _aliased(rt):
+        params = rt._params()
+        return all((not params[n].requires_grad) or (params[n].grad is not None and
+                   params[n].grad.data_ptr() == rt.grad_flat.data_ptr() + 4 * o)
+                   for n, o in zip(rt.grad_names, rt.grad_offs))
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)
@@ -47,10 +76,10 @@ class DistModule(Module):
             if rt.grad_flat is None:
                 continue
             params = rt._params()
-            ok = all((not params[n].requires_grad) or (params[n].grad is not None and
-                     params[n].grad.data_ptr() == rt.grad_flat.data_ptr() + 4 * o)
-                     for n, o in zip(rt.grad_names, rt.grad_offs))
-            if ok:
+            if id(rt) in self._pending:                       # already reduced on the side stream during backward
+                torch.cuda.current_stream().wait_event(self._pending.pop(id(rt))[1])
+                covered.update(id(params[n]) for n in rt.grad_names)
+            elif self._aliased(rt):
                 dist.all_reduce(rt.grad_flat)
                 covered.update(id(params[n]) for n in rt.grad_names)
         rest = [p.grad for p in self.module.parameters() if p.grad is not None and id(p) not in covered]

@@ -158,7 +158,7 @@ def text_embed_bwd(ids, dx, vocab):
     W = dx.shape[1]
     dtable = torch.zeros(vocab, W, device=dx.device, dtype=torch.float32)
     dpos = torch.zeros(L, W, device=dx.device, dtype=torch.float32)
-    _lib.check(lib.dc_text_embed_bwd(_ptr(ids), _ptr(dx), _ptr(dtable), _ptr(dpos), B, L, W, _stream()),
+    _lib.check(lib.dc_text_embed_bwd(_ptr(ids), _ptr(dx), _ptr(dtable), _ptr(dpos), None, B, L, W, _stream()),
                "dc_text_embed_bwd")
     return dtable, dpos
 

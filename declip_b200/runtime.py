@@ -58,6 +58,8 @@ class TowerRuntime:
         self._key = None          # (device, tuple of param data_ptrs)
         self._versions = None
         self.grad_flat = None
+        self._outstanding = 0     # forwards (under autograd) whose backward has not run yet
+        self.grad_ready_hook = None   # called (rt) when every outstanding backward of this tower has been enqueued
 
     # ------------------------------------------------------------------ parameter plumbing
     def _params(self):
@@ -233,6 +235,7 @@ class _TowerFunction(torch.autograd.Function):
     def forward(ctx, rt, inp, anchor, dense):
         params = rt._params()
         feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)
+        rt._outstanding += 1
         ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense = rt, cfg, inp_used, ws, params, dense
         if dense:
             return feats, words
@@ -240,8 +243,12 @@ class _TowerFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dfeats, dwords=None):
-        ctx.rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords)
+        rt = ctx.rt
+        rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords)
         ctx.ws = None
+        rt._outstanding = max(0, rt._outstanding - 1)
+        if rt._outstanding == 0 and rt.grad_ready_hook is not None:
+            rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
         return None, None, None, None
 
 

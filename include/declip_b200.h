@@ -117,9 +117,10 @@ int dc_vit_assemble(const void* patch_out, const float* cls, const float* pos, v
 /* text_transformer.py:188-190: x[b,l,:] = table[ids[b,l],:] + pos[l,:]; table,pos fp32; ids int64. */
 int dc_text_embed(const long long* ids, const float* table, const float* pos, void* x, int batch, int L,
                   int width, dc_stream_t stream);
-/* dtable[ids[b,l],:] += dx[b,l,:]  (fp32 atomics) ; dpos[l,:] += sum_b dx[b,l,:] */
-int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, int batch, int L,
-                      int width, dc_stream_t stream);
+/* dtable[ids[b,l],:] += dx[b,l,:]  (fp32 atomics) ; dpos[l,:] += sum_b dx[b,l,:].  last_row (int32 [batch], may be
+ * NULL) = row index of each sample's EOT token: rows after it have an exactly-zero gradient and are skipped. */
+int dc_text_embed_bwd(const long long* ids, const void* dx, float* dtable, float* dpos, const int* last_row, int batch,
+                      int L, int width, dc_stream_t stream);
 /* rows gather / scatter (cls token rows, EOT rows: visual_transformer.py:69, text_transformer.py:203):
  * dst[i,:] = src[idx[i],:]  /  dst[idx[i],:] = src[i,:]  (bf16 rows, int32 row indices). */
 int dc_gather_rows(const void* src, const int* idx, void* dst, int n, int width, dc_stream_t stream);
