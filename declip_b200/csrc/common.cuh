@@ -178,6 +178,13 @@ __device__ __forceinline__ float quick_gelu_grad(float x) {
   float s = sigmoidf_fast(1.702f * x);
   return s * (1.0f + 1.702f * x * (1.0f - s));
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -92,14 +92,6 @@ __device__ __forceinline__ void ln_bwd_load(LnRow<NV>& r, const bf16* __restrict
     if (dres != nullptr) r.dr[j] = *reinterpret_cast<const uint4*>(dres + base + c);
   }
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
-  float2 f;
-  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
-  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
-  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
-  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
-}
-
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,

@@ -7,10 +7,11 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from .modified_resnet import modified_resnet_R50
 from .text_transformer import text_transformers
 from .visual_transformer import visual_transformer_B32
 
-__all__ = ['clip_vitb32', 'CLIP']
+__all__ = ['clip_vitb32', 'clip_res50', 'CLIP']
 
 
 class CLIP(nn.Module):
@@ -66,5 +67,12 @@ class CLIP(nn.Module):
 def clip_vitb32(**kwargs):
     """clip.py:158-165."""
     image_encode = visual_transformer_B32(**kwargs['image_encode'])
+    text_encode = text_transformers(**kwargs['text_encode'])
+    return CLIP(image_encode, text_encode, **kwargs['clip'])
+
+
+def clip_res50(**kwargs):
+    """clip.py:149-156."""
+    image_encode = modified_resnet_R50(**kwargs['image_encode'])
     text_encode = text_transformers(**kwargs['text_encode'])
     return CLIP(image_encode, text_encode, **kwargs['clip'])

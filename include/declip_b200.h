@@ -186,6 +186,31 @@ int dc_groupmax_mean_bwd(const float* dout, int ldd, const unsigned char* arg, i
                          void* dG, int ldg, dc_stream_t stream);
 int dc_add_rows_f32(const float* src, const int* idx, float* dst, int n, int width, dc_stream_t stream);
 
+/* ------------------------------------------------------------------ ModifiedResNet support (modified_resnet.py)
+ * Activations are NHWC bf16 = [rows = B*H*W, C]; 1x1 convolutions are dc_gemm_bf16, 3x3 convolutions are
+ * im2col (K ordered (ky,kx,c)) + dc_gemm_bf16.
+ * stem conv1 (3->32, k3 s2 p1, modified_resnet.py:150): col bf16 [B*H/2*W/2, 32], k = (ky*3+kx)*3 + c, 27..31 zero. */
+int dc_im2col_stem(const float* images, long long sample_stride, void* col, int batch, int H, int W, dc_stream_t stream);
+/* 3x3 / pad 1 / stride 1: col bf16 [B*H*W, 9*C]; col2im is its transpose (the convolution's dgrad). */
+int dc_im2col3x3(const void* in, void* col, int batch, int H, int W, int C, dc_stream_t stream);
+int dc_col2im3x3(const void* dcol, void* din, int batch, int H, int W, int C, dc_stream_t stream);
+/* nn.AvgPool2d(2) on NHWC, forward (in [B,H,W,C] -> out [B,H/2,W/2,C]) or backward (in = d pooled, out = d input). */
+int dc_avgpool2(const void* in, void* out, int batch, int H, int W, int C, int backward, dc_stream_t stream);
+/* nn.BatchNorm2d in training mode over the rows of x bf16 [rows,C] (+ optional residual add, + optional ReLU):
+ * y = [relu]((x-mean)*rstd*gamma + beta [+ res]).  scratch: fp32 [2*C].  Running stats updated when non-NULL. */
+int dc_bn2d_fwd(const void* x, const float* gamma, const float* beta, const void* res, void* y, float* mean, float* rstd,
+                float* running_mean, float* running_var, float* scratch, long long rows, int C, float eps, float momentum,
+                int training, int relu, dc_stream_t stream);
+/* dx = BN'(g), g = dy * [y > 0]; dres (may be NULL) = g (gradient of the residual input); dgamma/dbeta accumulate. */
+int dc_bn2d_bwd(const void* dy, const void* x, const void* y, const float* gamma, const float* mean, const float* rstd,
+                void* dx, void* dres, float* dgamma, float* dbeta, float* scratch, long long rows, int C, int relu,
+                dc_stream_t stream);
+int dc_add_bf16(const void* a, const void* b, void* out, size_t n, dc_stream_t stream);
+/* AttentionPool2d token assembly (modified_resnet.py:72-74): tokens[b,0] = mean_p x[b,p] + pos[0];
+ * tokens[b,1+p] = x[b,p] + pos[1+p]; backward dx[b,p] = dtok[b,1+p] + dtok[b,0]/P. */
+int dc_attnpool_assemble(const void* x, const float* pos, void* tokens, int batch, int P, int C, dc_stream_t stream);
+int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, int C, dc_stream_t stream);
+
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.
  * Weight/grad tables are arrays of device pointers in the order documented in encoder.h order

@@ -31,6 +31,17 @@ def filip_inputs(c):
     return sd, images, mlm_ids, mlm_labels
 
 
+RES_CASES = {
+    "clip_res50_l1111_b4": dict(batch=4, layers=(1, 1, 1, 1), t_layers=2, embed_dim=1024, seed=6),
+}
+
+
+def res_inputs(c):
+    from . import synth
+    sd = synth.clip_res_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], layers=c["layers"], t_layers=c["t_layers"])
+    return sd, synth.synth_images(c["batch"], seed=c["seed"]), synth.synth_token_ids(c["batch"], seed=c["seed"])
+
+
 def declip_inputs(c):
     """Synthetic DeCLIP batch for a case: (state_dict, images[B,6,H,W], mlm_ids, mlm_labels, ids_aug, bank[dim,size])."""
     from . import synth

@@ -174,3 +174,26 @@ def reference_filip_step(sd, images6, mlm_ids, mlm_labels, embed_dim=768, v_laye
     loss.backward()
     return {"loss": loss.detach(), "parts": {k: v.detach() for k, v in parts.items()}, "out": out,
             "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}}, model
+
+
+def reference_clip_res_step(sd, images, ids, embed_dim=1024, layers=(3, 4, 6, 3), t_layers=12):
+    """Reference clip_res50 (use_sync_bn False) forward + ClipInfoCELoss + backward, CPU fp32."""
+    setup()
+    from prototype.model import model_entry
+    cfg = dict(type="clip_res50", kwargs=dict(
+        image_encode=dict(embed_dim=embed_dim, use_sync_bn=False, bn_group_size=1, layers=tuple(layers)),
+        text_encode=dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=embed_dim, transformer_layers=t_layers),
+        clip=dict(use_allgather=False)))
+    model = model_entry(cfg).train()
+    model.load_state_dict(sd, strict=True)
+    set_token_ids(model, ids)
+    B = images.shape[0]
+    li, lt = model({"images": images, "captions": [["x"]] * B})
+    loss, labels = clip_loss_fn()(li, lt)
+    loss.backward()
+    with torch.no_grad():
+        model.eval()
+    return {"loss": loss.detach(), "logits_per_image": li.detach(),
+            "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None},
+            "stats": {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k}}, model

@@ -155,3 +155,52 @@ def filip_extra_state_dict(seed=0, v_width=768, t_width=512, dense_dim=256, voca
         sd[name + ".weight"] = _randn(name + ".weight", seed, (o, i), i ** -0.5)
         sd[name + ".bias"] = _randn(name + ".bias", seed, (o,), 0.02)
     return sd
+
+
+def resnet_state_dict(seed=0, layers=(3, 4, 6, 3), width=64, embed_dim=1024, res=224, prefix="visual."):
+    """state_dict of ModifiedResNet (modified_resnet.py:109-190) under `prefix`, BatchNorm buffers included."""
+    sd = {}
+
+    def conv(name, cout, cin, k):
+        sd[prefix + name + ".weight"] = _randn(prefix + name, seed, (cout, cin, k, k), (cin * k * k) ** -0.5)
+
+    def bn(name, c):
+        sd[prefix + name + ".weight"] = 1.0 + _randn(prefix + name + ".w", seed, (c,), 0.1)
+        sd[prefix + name + ".bias"] = _randn(prefix + name + ".b", seed, (c,), 0.05)
+        sd[prefix + name + ".running_mean"] = torch.zeros(c)
+        sd[prefix + name + ".running_var"] = torch.ones(c)
+        sd[prefix + name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("conv1", width // 2, 3, 3); bn("bn1", width // 2)
+    conv("conv2", width // 2, width // 2, 3); bn("bn2", width // 2)
+    conv("conv3", width, width // 2, 3); bn("bn3", width)
+    inplanes = width
+    for li, (planes, blocks, stride) in enumerate(zip((width, width * 2, width * 4, width * 8), layers, (1, 2, 2, 2)), 1):
+        for bi in range(blocks):
+            p = "layer%d.%d." % (li, bi)
+            s = stride if bi == 0 else 1
+            conv(p + "conv1", planes, inplanes, 1); bn(p + "bn1", planes)
+            conv(p + "conv2", planes, planes, 3); bn(p + "bn2", planes)
+            conv(p + "conv3", planes * 4, planes, 1); bn(p + "bn3", planes * 4)
+            if s > 1 or inplanes != planes * 4:
+                conv(p + "downsample.0", planes * 4, inplanes, 1); bn(p + "downsample.1", planes * 4)
+            inplanes = planes * 4
+    feat = width * 32
+    sd[prefix + "attnpool.positional_embedding"] = _randn(prefix + "attnpool.pos", seed, ((res // 32) ** 2 + 1, feat),
+                                                          feat ** -0.5)
+    for n in ("k_proj", "q_proj", "v_proj"):
+        sd[prefix + "attnpool.%s.weight" % n] = _randn(prefix + "attnpool." + n, seed, (feat, feat), feat ** -0.5)
+        sd[prefix + "attnpool.%s.bias" % n] = _randn(prefix + "attnpool." + n + ".b", seed, (feat,), 0.02)
+    sd[prefix + "attnpool.c_proj.weight"] = _randn(prefix + "attnpool.c_proj", seed, (embed_dim, feat), feat ** -0.5)
+    sd[prefix + "attnpool.c_proj.bias"] = _randn(prefix + "attnpool.c_proj.b", seed, (embed_dim,), 0.02)
+    sd[prefix + "fc.weight"] = _randn(prefix + "fc", seed, (embed_dim, 2048), 2048 ** -0.5)
+    sd[prefix + "fc.bias"] = _randn(prefix + "fc.b", seed, (embed_dim,), 0.02)
+    return sd
+
+
+def clip_res_state_dict(seed=0, embed_dim=1024, layers=(3, 4, 6, 3), t_layers=12):
+    """clip_res50 (clip.py:149-156): ModifiedResNet image tower + the text transformer."""
+    full = clip_vit_state_dict(seed=seed, embed_dim=embed_dim, v_layers=0, t_layers=t_layers)
+    sd = {k: v for k, v in full.items() if not k.startswith("visual.")}
+    sd.update(resnet_state_dict(seed=seed, layers=layers, embed_dim=embed_dim))
+    return sd

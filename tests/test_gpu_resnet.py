@@ -1,0 +1,121 @@
+"""GPU parity of the ModifiedResNet image tower (BASELINE configs[3]: clip_res50) against the golden vectors of the
+reference's own clip_res50 and op-level checks of the convolution support kernels (through the C ABI)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-20)).item()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _nhwc(x):   # [B,C,H,W] -> [B*H*W, C] bf16
+    return x.permute(0, 2, 3, 1).reshape(-1, x.shape[1]).contiguous().bfloat16()
+
+
+def _nchw(y, B, H, W):
+    return y.float().view(B, H, W, -1).permute(0, 3, 1, 2)
+
+
+def test_conv_bn_pool_ops(cuda_dev):
+    from declip_b200 import functions_conv as C_
+    torch.manual_seed(0)
+    B, C, H, W = 3, 32, 14, 14
+    x = torch.randn(B, C, H, W, device=cuda_dev)
+    xh = _nhwc(x).requires_grad_(True)
+    xr = xh.detach().float().view(B, H, W, C).permute(0, 3, 1, 2).requires_grad_(True)
+    # 3x3 conv
+    w3 = (torch.randn(64, C, 3, 3, device=cuda_dev) * 0.1).requires_grad_(True)
+    y = C_.Conv3x3.apply(xh, w3, B, H, W)
+    yr = torch.nn.functional.conv2d(xr, w3, padding=1)
+    assert _rel(_nchw(y, B, H, W), yr) < 6e-3
+    g = torch.randn_like(yr)
+    y.backward(_nhwc(g))
+    gw, gx = w3.grad.clone(), xh.grad.clone()
+    w3.grad = None
+    yr.backward(g)
+    assert _cos(gw, w3.grad) > 0.999 and _cos(_nchw(gx, B, H, W), xr.grad) > 0.999
+    # 1x1 conv + BN(+res, relu) + avgpool
+    xh2 = _nhwc(x).requires_grad_(True)
+    xr2 = xh2.detach().float().view(B, H, W, C).permute(0, 3, 1, 2).requires_grad_(True)
+    w1 = (torch.randn(64, C, 1, 1, device=cuda_dev) * 0.2).requires_grad_(True)
+    bn = torch.nn.BatchNorm2d(64).to(cuda_dev).train()
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_(0, 0.2)
+    res = torch.randn(B, 64, H, W, device=cuda_dev)
+    resh = _nhwc(res).requires_grad_(True)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    z = C_.Conv1x1.apply(xh2, w1)
+    z = C_.BatchNorm2dNHWC.apply(z, resh, bn.weight, bn.bias, rm, rv, True, bn.eps, bn.momentum)
+    z = C_.AvgPool2.apply(z, B, H, W)
+    resr = resh.detach().float().view(B, H, W, 64).permute(0, 3, 1, 2).requires_grad_(True)
+    zr = torch.nn.functional.avg_pool2d(torch.relu(bn(torch.nn.functional.conv2d(xr2, w1)) + resr), 2)
+    assert _rel(_nchw(z, B, H // 2, W // 2), zr) < 1e-2
+    g = torch.randn_like(zr)
+    z.backward(_nhwc(g))
+    gw1, gx2, gres, gg, gb = w1.grad.clone(), xh2.grad.clone(), resh.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone()
+    w1.grad = None
+    bn.zero_grad()
+    zr.backward(g)
+    assert _cos(gw1, w1.grad) > 0.995 and _cos(_nchw(gx2, B, H, W), xr2.grad) > 0.995
+    assert _cos(_nchw(gres, B, H, W), resr.grad) > 0.999
+    assert _cos(gg, bn.weight.grad) > 0.995 and _cos(gb, bn.bias.grad) > 0.995
+    assert _rel(rm, bn.running_mean) < 2e-2 and _rel(rv, bn.running_var) < 2e-2
+    # stem conv from the fp32 NCHW image
+    img = torch.randn(2, 3, 224, 224, device=cuda_dev)
+    ws = (torch.randn(32, 3, 3, 3, device=cuda_dev) * 0.2).requires_grad_(True)
+    s = C_.StemConv.apply(img, ws)
+    sr = torch.nn.functional.conv2d(img, ws, stride=2, padding=1)
+    assert _rel(_nchw(s, 2, 112, 112), sr) < 6e-3
+    g = torch.randn_like(sr)
+    s.backward(_nhwc(g))
+    gws = ws.grad.clone()
+    ws.grad = None
+    sr.backward(g)
+    assert _cos(gws, ws.grad) > 0.999
+
+
+def test_clip_res50_step_matches_reference_golden(cuda_dev):
+    from declip_b200.loss_functions import ClipInfoCELoss
+    from declip_b200.model import model_entry
+    from oracle import golden
+    g = golden.load("clip_res50_l1111_b4")
+    c = g["case"]
+    cfg = dict(type='clip_res50', kwargs=dict(
+        image_encode=dict(embed_dim=c["embed_dim"], use_sync_bn=False, bn_group_size=1, layers=tuple(c["layers"])),
+        text_encode=dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=c["embed_dim"], transformer_layers=c["t_layers"]),
+        clip=dict(use_allgather=False)))
+    model = model_entry(cfg)
+    sd, images, ids = golden.res_inputs(c)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda_dev).train()
+    li, lt = model({"images": images.to(cuda_dev), "captions": None, "token_ids": ids.to(cuda_dev)})
+    loss, _ = ClipInfoCELoss()(li, lt)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - g["loss"]) <= 3e-2, (loss.item(), g["loss"])
+    assert _cos(li.cpu(), g["logits_per_image"]) > 0.998
+    params = dict(model.named_parameters())
+    assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
+    worst = []
+    for k, ref in g["grads"].items():
+        mine = params[k].grad.detach().float().reshape(-1).cpu()
+        if ref["norm"] < 1e-7:
+            continue
+        worst.append((_cos(mine[golden.sample_index(mine.numel())], ref["sample"]), mine.norm().item() / (ref["norm"] + 1e-20), k))
+    worst.sort()
+    txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:12])
+    # a batch of 4 through 13 BatchNorms (196 rows at 7x7) is the noisiest parity case of the repo: 0.93
+    assert worst[0][0] > 0.93, txt
+    assert sum(1 for w in worst if w[0] < 0.97) <= len(worst) // 10, txt
+    sdm = model.state_dict()
+    for k, v in g["stats"].items():
+        assert _rel(sdm[k].cpu(), v) < 5e-2, k

@@ -101,3 +101,19 @@ def test_filip_restatement_matches_reference_golden():
         mine = res["grads"][k].reshape(-1)
         samp = mine[golden.sample_index(mine.numel())]
         assert (samp - ref["sample"]).norm().item() <= 3e-3 * (ref["sample"].norm().item() + 1e-9) + 1e-7, k
+
+
+def test_resnet_restatement_matches_reference_golden():
+    from oracle import resnet_ref
+    g = golden.load("clip_res50_l1111_b4")
+    sd, images, ids = golden.res_inputs(g["case"])
+    res = resnet_ref.clip_res_step(sd, images, ids)
+    assert abs(res["loss"].item() - g["loss"]) <= 5e-5
+    torch.testing.assert_close(res["logits_per_image"], g["logits_per_image"], rtol=3e-4, atol=1e-3)
+    assert set(res["grads"]) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        mine = res["grads"][k].reshape(-1)
+        samp = mine[golden.sample_index(mine.numel())]
+        assert (samp - ref["sample"]).norm().item() <= 5e-3 * (ref["sample"].norm().item() + 1e-9) + 1e-6, k
+    for k, v in g["stats"].items():
+        torch.testing.assert_close(res["stats"][k], v, rtol=1e-4, atol=1e-5)

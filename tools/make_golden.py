@@ -17,7 +17,20 @@ from oracle import golden, ref_harness, synth  # noqa: E402
 def main():
     torch.set_num_threads(os.cpu_count() or 8)
     os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
-    names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES) + list(golden.FILIP_CASES))
+    names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES) + list(golden.FILIP_CASES) +
+                             list(golden.RES_CASES))
+    for name in [n for n in names if n in golden.RES_CASES]:
+        c = golden.RES_CASES[name]
+        t0 = time.time()
+        sd, images, ids = golden.res_inputs(c)
+        res, model = ref_harness.reference_clip_res_step(sd, images, ids, c["embed_dim"], c["layers"], c["t_layers"])
+        blob = {"case": c, "torch": torch.__version__,
+                "generator": "tools/make_golden.py via oracle/ref_harness.reference_clip_res_step (reference clip_res50, CPU fp32)",
+                "loss": res["loss"].item(), "logits_per_image": res["logits_per_image"].clone(),
+                "grads": golden.summarise_grads(res["grads"]), "stats": res["stats"]}
+        torch.save(blob, golden.path(name))
+        print("%s: loss %.6f, %d grads, %.1fs -> %.1f KB" % (name, blob["loss"], len(blob["grads"]), time.time() - t0,
+              os.path.getsize(golden.path(name)) / 1024))
     for name in [n for n in names if n in golden.FILIP_CASES]:
         c = golden.FILIP_CASES[name]
         t0 = time.time()
