@@ -491,18 +491,22 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
                                                      int label0, const long long* __restrict__ labels,
-                                                     float* __restrict__ loss_sum, int* __restrict__ top1,
-                                                     int* __restrict__ top5, float* __restrict__ lse_out) {
+                                                     const int* __restrict__ skip_col, float* __restrict__ loss_sum,
+                                                     int* __restrict__ top1, int* __restrict__ top5,
+                                                     float* __restrict__ lse_out) {
   __shared__ float s_red[8];
   const int row = blockIdx.x;
   const float* z = logits + static_cast<size_t>(row) * ld;
   const int label = labels ? static_cast<int>(labels[row]) : label0 + row;
+  const int skip = skip_col ? skip_col[row] : -1;   // column excluded from the softmax (NT-Xent self-similarity)
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, z[c]);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    if (c != skip) m = fmaxf(m, z[c]);
   m = block_reduce(m, s_red, true);
   const float zl = z[label];
   float s = 0.f, gt = 0.f;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    if (c == skip) continue;
     const float v = z[c];
     s += __expf(v - m);
     gt += (v > zl) ? 1.f : 0.f;
@@ -522,18 +526,21 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ l
 template <bool OUT_F32>
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, int ld, int rows, int cols,
                                                      int label0, const long long* __restrict__ labels,
-                                                     const float* __restrict__ lse,
+                                                     const int* __restrict__ skip_col, const float* __restrict__ lse,
                                                      const float* __restrict__ gscale_dev, float gscale_host,
                                                      void* __restrict__ dl, int lddl) {
   const int row = blockIdx.x;
   const float* z = logits + static_cast<size_t>(row) * ld;
   const int label = labels ? static_cast<int>(labels[row]) : label0 + row;
+  const int skip = skip_col ? skip_col[row] : -1;
   const float l = lse[row];
   const float gs = gscale_host * (gscale_dev ? *gscale_dev : 1.0f);
   const bool vec_ok = ((ld | lddl) & 1) == 0;
   for (int c = threadIdx.x * 2; c < cols; c += blockDim.x * 2) {
     const bool has2 = c + 1 < cols;
     float a = __expf(z[c] - l), b = has2 ? __expf(z[c + 1] - l) : 0.f;
+    if (c == skip) a = 0.f;
+    if (c + 1 == skip) b = 0.f;
     if (c == label) a -= 1.f;
     if (c + 1 == label) b -= 1.f;
     a *= gs;
@@ -725,25 +732,27 @@ int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, fl
 }
 
 int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
-                    float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream) {
+                    const int* skip_col, float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream) {
   if (rows <= 0) return 0;
   if (labels == nullptr && (label0 < 0 || label0 + rows > cols)) return set_error("ce_strip: labels out of range");
-  ce_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, loss_sum, top1,
-                                                                 top5, lse_out);
+  ce_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, skip_col,
+                                                                 loss_sum, top1, top5, lse_out);
   DC_CHECK_LAUNCH("ce_strip_fwd");
   return 0;
 }
 
 int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
-                    const float* lse, const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
-                    dc_stream_t stream) {
+                    const int* skip_col, const float* lse, const float* gscale_dev, float gscale_host, void* dlogits,
+                    int lddl, int out_f32, dc_stream_t stream) {
   if (rows <= 0) return 0;
   if (out_f32)
-    ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, lse,
-                                                                         gscale_dev, gscale_host, dlogits, lddl);
+    ce_bwd_kernel<true><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels,
+                                                                         skip_col, lse, gscale_dev, gscale_host, dlogits,
+                                                                         lddl);
   else
-    ce_bwd_kernel<false><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels, lse,
-                                                                          gscale_dev, gscale_host, dlogits, lddl);
+    ce_bwd_kernel<false><<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, rows, cols, label0, labels,
+                                                                          skip_col, lse, gscale_dev, gscale_host, dlogits,
+                                                                          lddl);
   DC_CHECK_LAUNCH("ce_strip_bwd");
   return 0;
 }

@@ -155,10 +155,10 @@ class ClipInfoCE(torch.autograd.Function):
         cnt = torch.zeros(2, device=li.device, dtype=torch.int32)
         lse_i = torch.empty(b, device=li.device, dtype=torch.float32)
         lse_t = torch.empty(b, device=li.device, dtype=torch.float32)
-        _lib.check(lib.dc_ce_strip_fwd(_PTR(li.data_ptr()), li.stride(0), b, n, label0, None, _PTR(acc.data_ptr()),
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(li.data_ptr()), li.stride(0), b, n, label0, None, None, _PTR(acc.data_ptr()),
                                        _PTR(cnt.data_ptr()), _PTR(cnt.data_ptr() + 4), _PTR(lse_i.data_ptr()),
                                        _stream()), "dc_ce_strip_fwd")
-        _lib.check(lib.dc_ce_strip_fwd(_PTR(lt.data_ptr()), lt.stride(0), b, n, label0, None, _PTR(acc.data_ptr() + 4), None,
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(lt.data_ptr()), lt.stride(0), b, n, label0, None, None, _PTR(acc.data_ptr() + 4), None,
                                        None, _PTR(lse_t.data_ptr()), _stream()), "dc_ce_strip_fwd")
         ctx.save_for_backward(li, lt, lse_i, lse_t)
         ctx.label0 = label0
@@ -175,7 +175,7 @@ class ClipInfoCE(torch.autograd.Function):
         dli = torch.empty(b, n, device=li.device, dtype=torch.float32)
         dlt = torch.empty(b, n, device=li.device, dtype=torch.float32)
         for z, lse, d in ((li, lse_i, dli), (lt, lse_t, dlt)):
-            _lib.check(lib.dc_ce_strip_bwd(_PTR(z.data_ptr()), z.stride(0), b, n, ctx.label0, None, _PTR(lse.data_ptr()),
+            _lib.check(lib.dc_ce_strip_bwd(_PTR(z.data_ptr()), z.stride(0), b, n, ctx.label0, None, None, _PTR(lse.data_ptr()),
                                            _PTR(g.data_ptr()), 1.0 / (2.0 * b), _PTR(d.data_ptr()), d.stride(0), 1,
                                            _stream()), "dc_ce_strip_bwd")
         return dli, dlt, None, None
@@ -412,7 +412,7 @@ class RowCE(torch.autograd.Function):
         acc = torch.zeros(1, device=logits.device, dtype=torch.float32)
         lse = torch.empty(n, device=logits.device, dtype=torch.float32)
         _lib.check(lib.dc_ce_strip_fwd(_PTR(logits.data_ptr()), logits.stride(0), n, cols, 0, _PTR(labels.data_ptr()),
-                                       _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
+                                       None, _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
                    "dc_ce_strip_fwd")
         ctx.save_for_backward(logits, labels, lse)
         ctx.cols = cols
@@ -426,7 +426,7 @@ class RowCE(torch.autograd.Function):
         g = g.contiguous().float().reshape(1)
         d = torch.zeros_like(logits)
         _lib.check(lib.dc_ce_strip_bwd(_PTR(logits.data_ptr()), logits.stride(0), n, ctx.cols, 0, _PTR(labels.data_ptr()),
-                                       _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(d.data_ptr()), d.stride(0), 1,
+                                       None, _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(d.data_ptr()), d.stride(0), 1,
                                        _stream()), "dc_ce_strip_bwd")
         return d, None, None
 
@@ -454,7 +454,7 @@ class MaskedLMHead(torch.autograd.Function):
         acc = torch.zeros(1, device=words.device, dtype=torch.float32)
         lse = torch.empty(n, device=words.device, dtype=torch.float32)
         _lib.check(lib.dc_ce_strip_fwd(_PTR(logits.data_ptr()), logits.stride(0), n, v, 0, _PTR(labels.data_ptr()),
-                                       _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
+                                       None, _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()), _stream()),
                    "dc_ce_strip_fwd")
         ctx.save_for_backward(x, rows, labels, w16, logits, lse)
         ctx.shape = (words.shape[0], v, vp, d)
@@ -469,7 +469,7 @@ class MaskedLMHead(torch.autograd.Function):
         g = g.contiguous().float().reshape(1)
         dl = torch.zeros(n, vp, device=x.device, dtype=torch.bfloat16)
         _lib.check(lib.dc_ce_strip_bwd(_PTR(logits.data_ptr()), logits.stride(0), n, v, 0, _PTR(labels.data_ptr()),
-                                       _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(dl.data_ptr()), dl.stride(0),
+                                       None, _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / n, _PTR(dl.data_ptr()), dl.stride(0),
                                        0, _stream()), "dc_ce_strip_bwd")
         dw = ops.gemm(dl, x, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)[:v]     # [v, d]
         db = ops.colsum(dl)[:v]
@@ -632,3 +632,64 @@ def token_scores(d1, d2, batch, n1, n2):
     _lib.check(lib.dc_token_scores(_PTR(d1.data_ptr()), _PTR(d2.data_ptr()), batch, n1, n2, dim, _PTR(s1.data_ptr()),
                                    _PTR(s2.data_ptr()), _stream()), "dc_token_scores")
     return s1, s2
+
+
+# =====================================================================================================================
+# NT-Xent family (loss_functions/nt_xent.py)
+# =====================================================================================================================
+class MatmulNT(torch.autograd.Function):
+    """s * A B^T (fp32 [R,E] x fp32 [C,E] -> fp32 [R,C]) on the tensor-core GEMM, gradients to both operands."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        a16 = _to_bf16_rows(a.float().contiguous(), a.shape[0])
+        cp = (b.shape[0] + 7) // 8 * 8
+        b16 = _to_bf16_rows(b.float().contiguous(), cp)                 # columns padded to a multiple of 8
+        out = ops.gemm(a16, b16, epilogue=ops.EPI_F32, alpha=float(scale))
+        ctx.save_for_backward(a16, b16)
+        ctx.scale, ctx.cols = float(scale), b.shape[0]
+        return out[:, :b.shape[0]] if cp != b.shape[0] else out
+
+    @staticmethod
+    def backward(ctx, ds):
+        a16, b16 = ctx.saved_tensors
+        cp = b16.shape[0]
+        if cp != ctx.cols:
+            pad = torch.zeros(ds.shape[0], cp, device=ds.device, dtype=torch.float32)
+            pad[:, :ctx.cols] = ds
+            ds = pad
+        ds16 = cast_bf16(ds.contiguous().float())
+        da = ops.gemm(ds16, b16, b_mn_major=True, epilogue=ops.EPI_F32, alpha=ctx.scale)
+        db = ops.gemm(ds16, a16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha=ctx.scale)[:ctx.cols]
+        return da, db, None
+
+
+class MaskedRowCE(torch.autograd.Function):
+    """sum_r CE(logits[r, all columns except skip[r]], labels[r]) / denom  — NT_Xent's [positive | negatives] CE."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, skip, denom):
+        lib = ops.lib_for(logits)
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
+        r, c = logits.shape
+        acc = torch.zeros(1, device=logits.device, dtype=torch.float32)
+        lse = torch.empty(r, device=logits.device, dtype=torch.float32)
+        _lib.check(lib.dc_ce_strip_fwd(_PTR(logits.data_ptr()), logits.stride(0), r, c, 0, _PTR(labels.data_ptr()),
+                                       _PTR(skip.data_ptr()), _PTR(acc.data_ptr()), None, None, _PTR(lse.data_ptr()),
+                                       _stream()), "dc_ce_strip_fwd")
+        ctx.save_for_backward(logits, labels, skip, lse)
+        ctx.denom = float(denom)
+        return acc[0] / denom
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, skip, lse = ctx.saved_tensors
+        lib = ops.lib_for(logits)
+        r, c = logits.shape
+        g = g.contiguous().float().reshape(1)
+        d = torch.empty(r, c, device=logits.device, dtype=torch.float32)
+        _lib.check(lib.dc_ce_strip_bwd(_PTR(logits.data_ptr()), logits.stride(0), r, c, 0, _PTR(labels.data_ptr()),
+                                       _PTR(skip.data_ptr()), _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / ctx.denom,
+                                       _PTR(d.data_ptr()), d.stride(0), 1, _stream()), "dc_ce_strip_bwd")
+        return d, None, None, None

@@ -55,7 +55,7 @@ class StripCE(torch.autograd.Function):
         lse = torch.empty(b, device=logits.device, dtype=torch.float32)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = ctypes.c_void_p
-        _lib.check(lib.dc_ce_strip_fwd(P(logits.data_ptr()), logits.stride(0), b, n, label0, None, P(acc.data_ptr()), None,
+        _lib.check(lib.dc_ce_strip_fwd(P(logits.data_ptr()), logits.stride(0), b, n, label0, None, None, P(acc.data_ptr()), None,
                                        None, P(lse.data_ptr()), st), "dc_ce_strip_fwd")
         ctx.save_for_backward(logits, lse)
         ctx.label0 = label0
@@ -72,7 +72,7 @@ class StripCE(torch.autograd.Function):
         d = torch.empty(b, n, device=logits.device, dtype=torch.float32)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = ctypes.c_void_p
-        _lib.check(lib.dc_ce_strip_bwd(P(logits.data_ptr()), logits.stride(0), b, n, ctx.label0, None, P(lse.data_ptr()),
+        _lib.check(lib.dc_ce_strip_bwd(P(logits.data_ptr()), logits.stride(0), b, n, ctx.label0, None, None, P(lse.data_ptr()),
                                        P(g.data_ptr()), 1.0 / b, P(d.data_ptr()), d.stride(0), 1, st), "dc_ce_strip_bwd")
         return d, None
 
@@ -94,3 +94,45 @@ class NTXentLoss(torch.nn.Module):
             zjs = F_.L2Normalize.apply(zjs, 1e-12)
         ab, ba = F_.StripLogits.apply(None, 1.0 / self.temperature, False, False, ((0, 1), (1, 0)), zis, zjs)
         return self.alpha_weight * StripCE.apply(ab, 0) + (1 - self.alpha_weight) * StripCE.apply(ba, 0)
+
+
+class NT_Xent(_Loss):
+    """loss_functions/nt_xent.py:6-44 (SimCLR): 2b x 2b cosine / T; for every row the positive is its other view and
+    the self-similarity is excluded — a row cross-entropy with one masked column, summed and divided by 2b."""
+
+    def __init__(self, batch_size, temperature=0.5):
+        super().__init__()
+        self.batch_size = batch_size
+        self.temperature = temperature
+
+    def forward(self, z_i, z_j):
+        b = self.batch_size
+        p = torch.cat((z_i, z_j), dim=0)
+        pn = F_.L2Normalize.apply(p, 1e-8)                                # nn.CosineSimilarity(dim=2), eps 1e-8
+        sim = F_.MatmulNT.apply(pn, pn, 1.0 / self.temperature)
+        r = torch.arange(2 * b, device=p.device)
+        labels = (r + b) % (2 * b)                                        # nt_xent.py:31-35: the other view
+        return F_.MaskedRowCE.apply(sim, labels.long(), r.int(), 2 * b)
+
+
+class NT_Xent_gather(_Loss):
+    """loss_functions/nt_xent.py:47-97 (SLIP): the 2b local rows against the 2N gathered columns; positives and the
+    excluded self column follow the rank-offset labels of nt_xent.py:74-86."""
+
+    def __init__(self, batch_size, temperature=0.1):
+        super().__init__()
+        self.batch_size = batch_size
+        self.temperature = temperature
+
+    def forward(self, z_i, z_ib, z_j, z_jb, temperature=None):
+        bs, l_bs = z_i.shape[0], z_ib.shape[0]
+        assert bs == self.batch_size
+        rank, _ = F_.dist_info()
+        p0 = F_.L2Normalize.apply(torch.cat((z_i, z_j), dim=0), 1e-8)
+        p1 = F_.L2Normalize.apply(torch.cat((z_ib, z_jb), dim=0), 1e-8)
+        sim = F_.MatmulNT.apply(p0, p1, 1.0 / self.temperature)          # the reference divides by self.temperature too
+        ids = torch.arange(bs, device=z_i.device)
+        lab = rank * bs + ids
+        labels = torch.cat((lab + l_bs, lab))                             # positives: nt_xent.py:77-78
+        skip = torch.cat((lab, lab + l_bs))                               # self columns: nt_xent.py:80,83
+        return F_.MaskedRowCE.apply(sim, labels.long(), skip.int(), 2 * bs)

@@ -7,10 +7,10 @@ To run the reference solvers unchanged, alias the package before importing them:
     import sys, declip_b200.model as m; sys.modules['prototype.model'] = m        
 """
 from .clip import CLIP, clip_res50, clip_vitb32  # noqa: F401
-from .declip import DECLIP, declip_vitb32  # noqa: F401
-from .filip import FILIP, filip_vitb32  # noqa: F401
+from .declip import DECLIP, declip_res50, declip_vitb32  # noqa: F401
+from .filip import FILIP, filip_res50, filip_vitb32  # noqa: F401
 
-_NOT_BUILT = ('declip_res50', 'filip_res50', 'slip_res50', 'slip_vitb32',
+_NOT_BUILT = ('slip_res50', 'slip_vitb32',
               'defilip_vitb32')
 
 

@@ -7,11 +7,12 @@ from torch import nn
 
 from .. import functions as F_
 from .clip import CLIP
+from .modified_resnet import modified_resnet_R50
 from .nn_memory_bank import NNMemoryBankModule
 from .text_transformer import text_transformers
 from .visual_transformer import visual_transformer_B32
 
-__all__ = ['declip_vitb32', 'DECLIP']
+__all__ = ['declip_vitb32', 'declip_res50', 'DECLIP']
 
 
 def _bn(bn, x, relu):
@@ -182,5 +183,12 @@ class DECLIP(CLIP):
 def declip_vitb32(**kwargs):
     """declip.py:348-355."""
     image_encode = visual_transformer_B32(**kwargs['image_encode'])
+    text_encode = text_transformers(**kwargs['text_encode'])
+    return DECLIP(image_encode, text_encode, **kwargs['clip'])
+
+
+def declip_res50(**kwargs):
+    """declip.py:339-346."""
+    image_encode = modified_resnet_R50(**kwargs['image_encode'])
     text_encode = text_transformers(**kwargs['text_encode'])
     return DECLIP(image_encode, text_encode, **kwargs['clip'])

@@ -7,10 +7,11 @@ from torch import nn
 
 from .. import functions as F_
 from .clip import CLIP
+from .modified_resnet import modified_resnet_R50
 from .text_transformer import text_transformers
 from .visual_transformer import visual_transformer_B32
 
-__all__ = ['filip_vitb32', 'FILIP']
+__all__ = ['filip_vitb32', 'filip_res50', 'FILIP']
 
 
 class FILIP(CLIP):
@@ -91,3 +92,10 @@ def filip_vitb32(**kwargs):
     image_encode = visual_transformer_B32(**kwargs['image_encode'])
     text_encode = text_transformers(**kwargs['text_encode'])
     return FILIP(image_encode, text_encode, **kwargs['clip'], dense_mapping_image=768)
+
+
+def filip_res50(**kwargs):
+    """filip.py:146-153."""
+    image_encode = modified_resnet_R50(**kwargs['image_encode'])
+    text_encode = text_transformers(**kwargs['text_encode'])
+    return FILIP(image_encode, text_encode, **kwargs['clip'], dense_mapping_image=2048)

@@ -136,17 +136,19 @@ int dc_l2norm_fwd(const float* x, void* y, float* y_f32, float* inv, int n, int 
 int dc_l2norm_bwd(const float* dy, const float* x, float* dx, int n, int dim, float eps, dc_stream_t stream);
 /* loss.py:40-50 (ClipInfoCELoss) on one logit strip, fused with misc.py:415-428 (accuracy top-1/top-5):
  * logits fp32 [rows,cols] (row stride ld), label[r] = labels ? labels[r] : label0 + r  (the int64 `labels`
- * array serves the DeCLIP masked-language-model head, declip.py:326-334).
+ * array serves the DeCLIP masked-language-model head, declip.py:326-334).  skip_col (int32 [rows], may be NULL):
+ * one column per row excluded from the softmax — the self-similarity of NT_Xent / NT_Xent_gather (nt_xent.py:19-26,
+ * 74-86), whose [positive | negatives] cross-entropy is exactly a row CE with that column masked.
  *   *loss_sum += sum_r (lse_r - logit[r,label_r])      (fp32 atomic; caller zeroes and divides by rows)
  *   *top1/*top5 += #{r : #(logit[r,:] > logit[r,label_r]) < 1 / < 5}   (may be NULL)
  *   lse_out[r] = log-sum-exp of row r (saved for backward). */
 int dc_ce_strip_fwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
-                    float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream);
+                    const int* skip_col, float* loss_sum, int* top1, int* top5, float* lse_out, dc_stream_t stream);
 /* dlogits([rows,cols], row stride lddl; bf16, or fp32 when out_f32) =
  *   gscale_host * (*gscale_dev) * (softmax(row) - onehot(label));  gscale_dev may be NULL (treated as 1). */
 int dc_ce_strip_bwd(const float* logits, int ld, int rows, int cols, int label0, const long long* labels,
-                    const float* lse, const float* gscale_dev, float gscale_host, void* dlogits, int lddl, int out_f32,
-                    dc_stream_t stream);
+                    const int* skip_col, const float* lse, const float* gscale_dev, float gscale_host, void* dlogits,
+                    int lddl, int out_f32, dc_stream_t stream);
 /* *out += sum_i a[i]*b[i]  (fp32; used for d logit_scale = exp(ls)/s * sum dlogits*logits, clip.py:133-141) */
 int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t stream);
 

@@ -164,3 +164,31 @@ def test_declip_step_matches_reference_golden(cuda_dev):
     assert model.nn_replacer_text.bank_ptr == g["bank_ptr"]
     tail = model.nn_replacer_text.bank[:2 * g["case"]["batch"]].t().cpu()
     assert _cos(tail, g["bank_tail"]) > 0.999
+
+
+def test_nt_xent_family(cuda_dev, monkeypatch):
+    """NT_Xent / NT_Xent_gather / NTXentLoss (a18) against the reference-pinned restatements."""
+    from declip_b200 import functions as F_
+    from declip_b200.loss_functions import NT_Xent, NT_Xent_gather, NTXentLoss
+    from oracle import declip_ref, golden, loss_ref
+    g = golden.load("nt_xent")
+    z_i, z_j, z_ib, z_jb, rank = loss_ref.inputs()
+    a, b = z_i.to(cuda_dev).requires_grad_(True), z_j.to(cuda_dev).requires_grad_(True)
+    l1 = NT_Xent(z_i.shape[0], 0.5)(a, b)
+    l1.backward()
+    assert abs(l1.item() - g["nt_xent"]) < 2e-2
+    assert _cos(a.grad.cpu(), g["nt_xent_grad"]) > 0.995
+    monkeypatch.setattr(F_, "dist_info", lambda: (rank, 3))
+    c, d = z_i.to(cuda_dev).requires_grad_(True), z_j.to(cuda_dev).requires_grad_(True)
+    l2 = NT_Xent_gather(z_i.shape[0], 0.1)(c, z_ib.to(cuda_dev), d, z_jb.to(cuda_dev))
+    l2.backward()
+    assert abs(l2.item() - g["nt_xent_gather"]) < 5e-2, (l2.item(), g["nt_xent_gather"])
+    assert _cos(c.grad.cpu(), g["nt_xent_gather_grad_i"]) > 0.99 and _cos(d.grad.cpu(), g["nt_xent_gather_grad_j"]) > 0.99
+    monkeypatch.undo()
+    e, f = z_i.to(cuda_dev).requires_grad_(True), z_j.to(cuda_dev).requires_grad_(True)
+    l3 = NTXentLoss(z_i.shape[0])(e, f)
+    l3.backward()
+    er, fr = z_i.clone().requires_grad_(True), z_j.clone().requires_grad_(True)
+    l3r = declip_ref.nt_xent(er, fr)
+    l3r.backward()
+    assert abs(l3.item() - l3r.item()) < 3e-2 and _cos(e.grad.cpu(), er.grad) > 0.99

@@ -117,3 +117,19 @@ def test_resnet_restatement_matches_reference_golden():
         assert (samp - ref["sample"]).norm().item() <= 5e-3 * (ref["sample"].norm().item() + 1e-9) + 1e-6, k
     for k, v in g["stats"].items():
         torch.testing.assert_close(res["stats"][k], v, rtol=1e-4, atol=1e-5)
+
+
+def test_nt_xent_restatements_match_reference_golden():
+    from oracle import loss_ref
+    g = golden.load("nt_xent")
+    z_i, z_j, z_ib, z_jb, rank = loss_ref.inputs()
+    a, b = z_i.clone().requires_grad_(True), z_j.clone().requires_grad_(True)
+    l1 = loss_ref.nt_xent(a, b)
+    l1.backward()
+    assert abs(l1.item() - g["nt_xent"]) < 1e-5
+    torch.testing.assert_close(a.grad, g["nt_xent_grad"], rtol=1e-4, atol=1e-6)
+    c, d = z_i.clone().requires_grad_(True), z_j.clone().requires_grad_(True)
+    l2 = loss_ref.nt_xent_gather(c, z_ib, d, z_jb, rank=rank)
+    l2.backward()
+    assert abs(l2.item() - g["nt_xent_gather"]) < 1e-5
+    torch.testing.assert_close(c.grad, g["nt_xent_gather_grad_i"], rtol=1e-4, atol=1e-6)

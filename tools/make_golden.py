@@ -19,6 +19,25 @@ def main():
     os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
     names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES) + list(golden.FILIP_CASES) +
                              list(golden.RES_CASES))
+    if "nt_xent" in names or not sys.argv[1:]:
+        from oracle import loss_ref
+        ref_harness.setup()
+        os.environ["SLURM_PROCID"], os.environ["SLURM_NTASKS"] = "1", "3"     # link.get_rank() reads SLURM env
+        from prototype.loss_functions import NT_Xent, NT_Xent_gather
+        z_i, z_j, z_ib, z_jb, rank = loss_ref.inputs()
+        a, b = z_i.clone().requires_grad_(True), z_j.clone().requires_grad_(True)
+        l1 = NT_Xent(z_i.shape[0], 0.5)(a, b)
+        l1.backward()
+        c, d = z_i.clone().requires_grad_(True), z_j.clone().requires_grad_(True)
+        l2 = NT_Xent_gather(z_i.shape[0], 0.1)(c, z_ib, d, z_jb)
+        l2.backward()
+        del os.environ["SLURM_PROCID"], os.environ["SLURM_NTASKS"]
+        torch.save({"generator": "tools/make_golden.py nt_xent (reference NT_Xent / NT_Xent_gather, CPU fp32)",
+                    "nt_xent": l1.item(), "nt_xent_grad": a.grad.clone(), "nt_xent_gather": l2.item(),
+                    "nt_xent_gather_grad_i": c.grad.clone(), "nt_xent_gather_grad_j": d.grad.clone(), "rank": rank},
+                   golden.path("nt_xent"))
+        print("nt_xent: %.6f  nt_xent_gather: %.6f" % (l1.item(), l2.item()))
+    names = [n for n in names if n != "nt_xent"]
     for name in [n for n in names if n in golden.RES_CASES]:
         c = golden.RES_CASES[name]
         t0 = time.time()
