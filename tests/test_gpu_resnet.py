@@ -128,3 +128,48 @@ def test_clip_res50_step_matches_reference_golden(cuda_dev):
     sdm = model.state_dict()
     for k, v in g["stats"].items():
         assert _rel(sdm[k].cpu(), v) < 5e-2, k
+
+
+@pytest.mark.parametrize("kind", ["declip_res50", "filip_res50"])
+def test_res50_wrappers_run(cuda_dev, kind):
+    """declip_res50 / filip_res50 (declip.py:339-346, filip.py:146-153): the ResNet tower behind the DeCLIP / FILIP
+    heads — forward dict + backward produce finite losses and gradients for every trainable parameter."""
+    from declip_b200.loss_functions import ClipInfoCELoss, SimsiamLoss
+    from declip_b200.model import model_entry
+    from oracle import synth
+    torch.manual_seed(0)
+    E = 1024
+    clip_kw = dict(use_allgather=True, text_mask_type='MLM', feature_dim=E)
+    if kind == "declip_res50":
+        clip_kw.update(return_nn_bank=True, nn_size=256)
+    else:
+        clip_kw.update(return_dense=True, select_topk=True, mask_rate=0.5, patch_number=14)
+    cfg = dict(type=kind, kwargs=dict(
+        image_encode=dict(embed_dim=E, use_sync_bn=False, bn_group_size=1, layers=(1, 1, 1, 1)),
+        text_encode=dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=E, transformer_layers=1), clip=clip_kw))
+    model = model_entry(cfg).to(cuda_dev).train()
+    B = 8
+    ids = synth.synth_token_ids(B, seed=1)
+    mlm = synth.synth_mlm(ids, seed=1)
+    batch = {"images": torch.randn(B, 6, 224, 224, device=cuda_dev), "token_ids": ids.to(cuda_dev),
+             "token_ids_aug": synth.synth_token_ids(B, seed=2).to(cuda_dev), "mlm": (mlm[0].to(cuda_dev), mlm[1])}
+    out = model(batch, return_dict=True)
+    crit = ClipInfoCELoss()
+    if kind == "declip_res50":
+        li1, li2, lt1, lt2 = out["logits"]
+        p1, p2, z1, z2 = out["simsiam_features"]
+        n1, n2, n1a, n2a = out["nn_text_logits"]
+        loss = crit(li1, lt1)[0] + crit(li2, lt2)[0] + SimsiamLoss()(p1, z1, p2, z2) + out["text_self_supervised"] + \
+            crit(n1, n1a)[0]
+    else:
+        loss = crit(*out["logits"])[0] + crit(*out["dense_logits"])[0]
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item()
+    missing = [k for k, p in model.named_parameters() if p.requires_grad and p.grad is None]
+    unused = {"text_label_predictor.weight", "text_label_predictor.bias", "visual.fc.weight", "visual.fc.bias"}
+    assert set(missing) <= unused, missing
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), k
