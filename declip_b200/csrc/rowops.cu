@@ -605,7 +605,8 @@ int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
                      dc_stream_t stream) {
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 4);
+  // one resident block per SM (188-253 registers/thread): more blocks only multiply the per-block atomics epilogue
+  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 1);
   const bf16* dyp = static_cast<const bf16*>(dy);
   const bf16* xp = static_cast<const bf16*>(x);
   const bf16* rp = static_cast<const bf16*>(dres);
