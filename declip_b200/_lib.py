@@ -58,6 +58,7 @@ SIGNATURES = {
     "dc_sm_count": (c_int, []),
     "dc_launch_count": (c_ll, []),
     "dc_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "dc_set_gemm_2cta": (c_int, [c_int]),
     "dc_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),
     "dc_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -165,7 +166,14 @@ def init(device_index):
     if device_index not in _inited_devices:
         check(lib.dc_init(int(device_index)), "dc_init")
         _inited_devices.add(device_index)
+        if os.environ.get("DC_GEMM_2CTA") is not None:
+            lib.dc_set_gemm_2cta(int(os.environ["DC_GEMM_2CTA"] != "0"))
     return lib
+
+
+def set_gemm_2cta(enable):
+    """Select the cta_group::2 GEMM (256x256 cluster tiles) where the problem is large enough; returns the old value."""
+    return int(load().dc_set_gemm_2cta(int(bool(enable))))
 
 
 def launch_count():

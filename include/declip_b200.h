@@ -71,6 +71,9 @@ typedef struct {
                                  clip.py:133-134) so no host sync is needed; NULL = 1 */
 } dc_gemm_args;
 int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
+/* Select the 2-CTA (cta_group::2, 256x256 cluster tile) variant for problems with M >= 256 and N >= 256; returns the
+ * previous setting.  Default 0 (1-CTA 128x256 kernel). */
+int dc_set_gemm_2cta(int enable);
 
 /* ------------------------------------------------------------------ row kernels (HBM-bound)
  * LayerNorm over the last dim (eps 1e-5): base_transformer.py:10-18, visual_transformer.py:63,69,
