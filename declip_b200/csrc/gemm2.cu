@@ -7,8 +7,8 @@
 // (2 stages), drained by that CTA's 8 epilogue warps with the same fused epilogue as gemm.cu.
 //
 // Cross-CTA synchronisation:
-//   full[s]   (leader smem, count 2): leader arrive.expect_tx(2 x 32 KiB) + remote arrive from the peer producer;
-//             both CTAs' TMA loads complete_tx on the LEADER's barrier (.cta_group::2 TMA with a cluster address).
+//   full[s]   (leader smem, count 1): leader arrive.expect_tx(2 x 32 KiB); both CTAs' TMA loads complete_tx on the
+//             LEADER's barrier (.cta_group::2 TMA with a cluster address) — the peer never arrives explicitly.
 //   empty[s], tfull[a] (each CTA, count 1): tcgen05.commit.cta_group::2 ... multicast::cluster, mask 0b11.
 //   tempty[a] (leader smem, count 16): one arrive per epilogue warp of BOTH CTAs (remote arrive via mapa).
 #include <string.h>
@@ -109,7 +109,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < G2_STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);   // leader expect_tx arrive + peer remote arrive (only the leader's copy is used)
+      mbar_init(&full_bar[s], 1);   // the leader's expect_tx arrive; both CTAs' TMA loads complete_tx on the leader's copy
       mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA thread
     }
     for (int s = 0; s < 2; ++s) {
@@ -145,8 +145,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          // Only the leader arrives (expecting the bytes of BOTH CTAs); the peer's loads just complete_tx on the
+          // leader's barrier.  A per-stage remote arrive.release.cluster from the peer costs a cluster-scope fence
+          // (ERRBAR/MEMBAR, 7 % of all stall samples in the first version) and halved the tensor-pipe utilisation.
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
-          else mbar_arrive_cluster(full_leader);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
           uint8_t* sb = sa + G2_A_BYTES;
           if (!A_MN) {
