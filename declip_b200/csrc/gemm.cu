@@ -26,7 +26,7 @@
 namespace dc {
 
 int gemm2_bf16(const dc_gemm_args& a, cudaStream_t stream);   // gemm2.cu
-static std::atomic<int> g_gemm_2cta{0};
+static std::atomic<int> g_gemm_2cta{1};   // cta_group::2 by default where the problem is >= one 256x256 cluster tile
 
 template <int BN>
 struct GemmCfg {

@@ -33,6 +33,25 @@ def test_gemm_majors(cuda_dev, a_mn, b_mn, shape):
         assert _rel(got, want) < 1e-5, (shape, a_mn, b_mn, bn)     # fp32 accumulate of exact bf16 products
 
 
+@pytest.mark.parametrize("two_cta", [0, 1])
+def test_gemm_1cta_and_2cta_variants(cuda_dev, two_cta):
+    """Both GEMM kernels (gemm.cu 128x256 per CTA, gemm2.cu 256x256 per CTA pair) on cluster-tile-sized problems."""
+    from declip_b200 import _lib, ops
+    ops.lib_for(torch.zeros(1, device=cuda_dev))
+    old = _lib.set_gemm_2cta(bool(two_cta))
+    try:
+        torch.manual_seed(7)
+        for (a_mn, b_mn) in ((0, 0), (0, 1), (1, 1)):
+            for (M, N, K) in ((256, 256, 64), (1000, 2304, 768), (3072, 768, 1544), (304, 520, 200)):
+                a = (torch.randn((K, M) if a_mn else (M, K), device=cuda_dev) * 0.5).bfloat16()
+                b = (torch.randn((K, N) if b_mn else (N, K), device=cuda_dev) * 0.5).bfloat16()
+                want = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+                got = ops.gemm(a, b, a_mn_major=bool(a_mn), b_mn_major=bool(b_mn), epilogue=ops.EPI_F32)
+                assert _rel(got, want) < 1e-5, (two_cta, a_mn, b_mn, M, N, K)
+    finally:
+        _lib.set_gemm_2cta(bool(old))
+
+
 def test_gemm_epilogues(cuda_dev):
     from declip_b200 import ops
     torch.manual_seed(1)
