@@ -35,8 +35,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int STAGING_BYTES = EPI_WARPS * 2048;       // per-epilogue-warp 32x32 bf16 TMA-store staging
-  static constexpr int BIAS_BYTES = EPI_WARPS * (BN / 2) * 4;  // per-epilogue-warp bias slice
+  static constexpr int STAGING_BYTES = EPI_WARPS * 4096;       // per-epilogue-warp 2 x (32x32 bf16) TMA-store staging
+  static constexpr int BIAS_BYTES = 0;                          // bias is broadcast by warp shuffles
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 /*barriers*/ + BIAS_BYTES +
                                     1024 /*align slack*/;
 };
@@ -57,7 +57,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias_all = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,8 +168,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;     // which half of the tile's columns
     constexpr int NCH = BN / 64;          // 32-column chunks per warp
-    float* s_bias = s_bias_all + (warp - 4) * (BN / 2);
-    uint8_t* stage = staging + (warp - 4) * 2048;
+    uint8_t* stage = staging + (warp - 4) * 4096;
+    uint32_t sidx = 0;
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
     uint32_t aphase = 0;
@@ -184,14 +183,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(as * BN + half * (BN / 2));
 #define DC_EPI_CASE(E) \
-  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage, &tfull_bar[as], aphase); break
+  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage, &tfull_bar[as], aphase); break
       switch (p.epi) {
         DC_EPI_CASE(DC_EPI_BF16);
         DC_EPI_CASE(DC_EPI_BF16_GELU);
         DC_EPI_CASE(DC_EPI_BF16_RESID);
         DC_EPI_CASE(DC_EPI_BF16_DGELU);
         DC_EPI_CASE(DC_EPI_F32);
-        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage,
+        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage,
                                                        &tfull_bar[as], aphase); break;
       }
 #undef DC_EPI_CASE

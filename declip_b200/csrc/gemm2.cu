@@ -22,8 +22,8 @@ constexpr int G2_A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows
 constexpr int G2_B_BYTES = (BN2 / 2) * BK * 2;   // 16 KiB: this CTA's half of the 256 N rows
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_TMEM_COLS = 2 * BN2;
-constexpr int G2_STAGING_BYTES = EPI_WARPS * 2048;
-constexpr int G2_BIAS_BYTES = EPI_WARPS * (BN2 / 2) * 4;
+constexpr int G2_STAGING_BYTES = EPI_WARPS * 4096;   // 2 x (32x32 bf16) per epilogue warp
+constexpr int G2_BIAS_BYTES = 0;                      // bias is broadcast by warp shuffles
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_STAGING_BYTES + 256 + G2_BIAS_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -42,7 +42,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // relaxed: the TMEM reads this arrival publishes are already complete (tcgen05.wait::ld) and fenced with
+  // tcgen05.fence::before_thread_sync; a release at cluster scope costs an ERRBAR + MEMBAR.ALL (22 % of the stall
+  // samples of the first 2-CTA version) and delays the MMA warp's re-use of the accumulator stage.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tm, uint32_t mbar_cluster_addr, int c0, int c1) {
   asm volatile(
@@ -92,7 +95,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tfull_bar = empty_bar + G2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bias_all = reinterpret_cast<float*>(staging + G2_STAGING_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,8 +212,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int NCH = BN2 / 64;
-    float* s_bias = s_bias_all + (warp - 4) * (BN2 / 2);
-    uint8_t* stage_buf = staging + (warp - 4) * 2048;
+    uint8_t* stage_buf = staging + (warp - 4) * 4096;
+    uint32_t sidx = 0;
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
     uint32_t aphase = 0;
@@ -225,14 +227,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(as * BN2 + half * (BN2 / 2));
 #define DC_EPI_CASE(E) \
-  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage_buf, &tfull_bar[as], aphase); break
+  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf, &tfull_bar[as], aphase); break
       switch (p.epi) {
         DC_EPI_CASE(DC_EPI_BF16);
         DC_EPI_CASE(DC_EPI_BF16_GELU);
         DC_EPI_CASE(DC_EPI_BF16_RESID);
         DC_EPI_CASE(DC_EPI_BF16_DGELU);
         DC_EPI_CASE(DC_EPI_F32);
-        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, s_bias, stage_buf,
+        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf,
                                                        &tfull_bar[as], aphase); break;
       }
 #undef DC_EPI_CASE

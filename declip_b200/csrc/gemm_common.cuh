@@ -30,17 +30,21 @@ constexpr int EPI_WARPS = 8;
 // ---------------------------------------------------------------------------------------------- epilogue
 // One epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) x BN/2 columns of a tile, processed in
 // 32-column chunks.  Everything the math needs from global memory is fetched BEFORE it is needed: the bias slice
-// is loaded to registers before the warp blocks on the accumulator barrier and parked in per-warp shared memory;
+// is loaded to registers before the warp blocks on the accumulator barrier and broadcast by warp shuffles;
 // the aux operand (residual / pre-activation) of chunk c+1 is in flight while chunk c is processed.
-// bf16 outputs leave through a per-warp 2 KiB staging buffer (64-byte swizzle, conflict-free st.shared.v4) and one
+// bf16 outputs leave through two per-warp 2 KiB staging buffers (64-byte swizzle, conflict-free st.shared.v4) and one
 // TMA store per 32x32 chunk: fully coalesced 64-byte row segments, OOB rows/cols clipped by the TMA unit, and the
 // LSU is free for the next chunk.  fp32 outputs (logit strips, features, split-K wgrad atomics) are written
 // directly.  The epilogue mode is a compile-time parameter (one branch per tile).
-__device__ __forceinline__ void stage_store_chunk(const float (&v)[32], uint8_t* stage, const CUtensorMap* tm, int col0,
-                                                  int row0) {
+__device__ __forceinline__ void stage_store_chunk(const float (&v)[32], uint8_t* stage, uint32_t& sidx,
+                                                  const CUtensorMap* tm, int col0, int row0) {
   const int lane = lane_id();
-  if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging buffer
+  // two 2 KiB staging buffers per warp: the store issued two chunks ago (same buffer) must have been read out,
+  // the previous one (other buffer) may still be in flight
+  if (lane == 0) bulk_wait_read1();
   __syncwarp();
+  stage += (sidx & 1u) * 2048;
+  sidx ^= 1u;
   uint8_t* rowp = stage + lane * 64;
   const int sw = (lane >> 1) & 3;    // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
@@ -78,7 +82,7 @@ __device__ __forceinline__ float chunk_colsum(float (&v)[32]) {
 // Waits for the accumulator, then drains this warp's 32 rows x (NCH * 32) columns starting at column `colbase`.
 template <int EPI, int NCH>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tm_out, const CUtensorMap* tm_out2,
-                                              float alpha, uint32_t taddr, int row0, int colbase, float* s_bias,
+                                              float alpha, uint32_t taddr, int row0, int colbase, uint32_t& sidx,
                                               uint8_t* stage, uint64_t* tfull, uint32_t parity) {
   constexpr bool HAS_AUX = (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU);
   constexpr bool HAS_BIAS = (EPI != DC_EPI_F32_ATOMIC && EPI != DC_EPI_BF16_DGELU);
@@ -106,11 +110,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
   }
   mbar_wait(tfull, parity);
   tc_fence_after();
-  if (HAS_BIAS) {
-    __syncwarp();
-    if (lane < NCH * 8) *reinterpret_cast<float4*>(s_bias + lane * 4) = bv;
-    __syncwarp();
-  }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col0 = colbase + c * 32;
@@ -131,11 +130,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-      if (use_bias) {
+      if (use_bias) {   // lane (c*8 + g) holds the bias of columns c*32 + 4g .. 4g+3: broadcast by shuffle, no smem
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c * 32 + g * 4);
-          v[4 * g + 0] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+          const int src = c * 8 + g;
+          v[4 * g + 0] += __shfl_sync(0xffffffffu, bv.x, src);
+          v[4 * g + 1] += __shfl_sync(0xffffffffu, bv.y, src);
+          v[4 * g + 2] += __shfl_sync(0xffffffffu, bv.z, src);
+          v[4 * g + 3] += __shfl_sync(0xffffffffu, bv.w, src);
         }
       }
       if (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU) {
@@ -156,11 +158,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
       }
       if (OUT_BF16) {
         if (EPI == DC_EPI_BF16_GELU) {
-          stage_store_chunk(v, stage, tm_out2, col0, row0);   // pre-activation u (saved for backward)
+          stage_store_chunk(v, stage, sidx, tm_out2, col0, row0);   // pre-activation u (saved for backward)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
         }
-        stage_store_chunk(v, stage, tm_out, col0, row0);
+        stage_store_chunk(v, stage, sidx, tm_out, col0, row0);
         if (p.colsum != nullptr) {                            // fused bias gradient: colsum += sum_rows out
           if (!row_ok) {
 #pragma unroll
