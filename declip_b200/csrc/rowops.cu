@@ -766,3 +766,65 @@ int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Fused multi-tensor AdamW (decoupled weight decay, torch.optim.AdamW semantics) — the optimiser step of the
+// reference configs (experiments/*/config.yaml: optimizer type AdamW; prototype/optimizer/__init__.py:18-26).
+// One launch for every parameter tensor: blockIdx.y selects the tensor from a device table.
+namespace dc {
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const dc_adamw_entry* __restrict__ table, float beta1,
+                                                          float beta2, float eps, float bc1, float bc2) {
+  const dc_adamw_entry e = table[blockIdx.y];
+  float* __restrict__ p = e.param;
+  const float* __restrict__ g = e.grad;
+  float* __restrict__ m = e.exp_avg;
+  float* __restrict__ v = e.exp_avg_sq;
+  const size_t n = e.numel;
+  const float lr = e.lr, wd = e.weight_decay;
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nv = n >> 2;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pp[k] *= 1.0f - lr * wd;
+      mp[k] = beta1 * mp[k] + (1.0f - beta1) * gp[k];
+      vp[k] = beta2 * vp[k] + (1.0f - beta2) * gp[k] * gp[k];
+      const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+      pp[k] -= step_size * mp[k] / denom;
+    }
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const size_t i = (nv << 2) + threadIdx.x;
+    float pk = p[i] * (1.0f - lr * wd);
+    const float mk = beta1 * m[i] + (1.0f - beta1) * g[i];
+    const float vk = beta2 * v[i] + (1.0f - beta2) * g[i] * g[i];
+    pk -= step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+    p[i] = pk; m[i] = mk; v[i] = vk;
+  }
+}
+}  // namespace dc
+
+extern "C" int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, float beta1,
+                              float beta2, float eps, int step, dc_stream_t stream) {
+  if (n_tensors <= 0) return 0;
+  if (step < 1) return dc::set_error("adamw: step must be >= 1");
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  int bx = static_cast<int>((max_numel / 4 + 255) / 256);
+  if (bx > 128) bx = 128;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_tensors);
+  dc::adamw_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, beta1, beta2, eps, bc1, bc2);
+  DC_CHECK_LAUNCH("adamw_multi");
+  return 0;
+}

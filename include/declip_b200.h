@@ -97,6 +97,17 @@ typedef struct { const float* src; void* dst; unsigned long long numel; } dc_cas
 int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsigned long long max_numel,
                            dc_stream_t stream);
 
+/* Fused multi-tensor AdamW step (torch.optim.AdamW semantics: p *= 1 - lr*wd; Adam moments; bias correction from
+ * `step`): the optimiser of the reference configs (config.yaml optimizer.type AdamW).  table (device): one entry per
+ * parameter tensor, fp32 everywhere; lr / weight_decay per entry carry the reference's param groups
+ * (utils/misc.py:267-412: no decay on biases / norms / logit_scale). */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  unsigned long long numel; float lr; float weight_decay;
+} dc_adamw_entry;
+int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, float beta1,
+                   float beta2, float eps, int step, dc_stream_t stream);
+
 /* ------------------------------------------------------------------ attention (L <= 80, head_dim 64)
  * softmax(q k^T / sqrt(64) [+ causal mask]) v per (sample, head): base_transformer.py:44-48 via
  * nn.MultiheadAttention; causal mask text_transformer.py:136-142.

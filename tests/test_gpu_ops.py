@@ -207,3 +207,25 @@ def test_head_functions(cuda_dev):
         p1, p5 = crit.accuracy()
         r1, r5 = clip_ref.accuracy(li.detach().cpu(), labels_r)
         assert abs(p1.item() - r1.item()) < 1e-3 and abs(p5.item() - r5.item()) < 1e-3
+
+
+def test_fused_adamw_matches_torch(cuda_dev):
+    from declip_b200.optim import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(768, 3072), (3072,), (1,), (49409, 16), (50, 768), (7,)]
+    ps = [torch.randn(s, device=cuda_dev).requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    groups = lambda xs: [dict(params=xs[:3], weight_decay=0.1), dict(params=xs[3:], weight_decay=0.0, lr=3e-4)]
+    mine = FusedAdamW(groups(ps), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    ref = torch.optim.AdamW(groups(qs), lr=1e-3, betas=(0.9, 0.98), eps=1e-6)
+    for it in range(4):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        if it == 2:                                   # a scheduler changing the lr forces a table rebuild
+            for o in (mine, ref):
+                o.param_groups[0]["lr"] = 5e-4
+        mine.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (p - q).abs().max()
