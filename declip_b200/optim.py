@@ -17,6 +17,7 @@ class FusedAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._table = None
         self._sig = None
+        self._gbuf = {}      # small parameters whose autograd gradient is a fresh tensor every step (logit_scale)
 
     def _build(self, plist):
         n = len(plist)
@@ -25,7 +26,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for i, (p, group) in enumerate(plist):
             st = self.state[p]
             entries[i].param = p.data_ptr()
-            entries[i].grad = p.grad.data_ptr()
+            entries[i].grad = self._grad_ptr(p)
             entries[i].exp_avg = st["exp_avg"].data_ptr()
             entries[i].exp_avg_sq = st["exp_avg_sq"].data_ptr()
             entries[i].numel = p.numel()
@@ -35,6 +36,20 @@ class FusedAdamW(torch.optim.Optimizer):
         dev = plist[0][0].device
         self._table = torch.frombuffer(bytearray(bytes(entries)), dtype=torch.uint8).to(dev)
         self._n, self._max = n, mx
+
+    def _grad_ptr(self, p):
+        g = self._gbuf.get(p)
+        return g.data_ptr() if g is not None else p.grad.data_ptr()
+
+    def _stabilise_small_grads(self, plist):
+        """Gradients produced by autograd (not the towers' flat buffers) live in a new tensor each step; copying the
+        small ones into persistent buffers keeps the device pointer table valid from step to step."""
+        for p, _ in plist:
+            if p.numel() <= 4096:
+                buf = self._gbuf.get(p)
+                if buf is None:
+                    buf = self._gbuf[p] = torch.empty_like(p.grad)
+                buf.copy_(p.grad)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -63,7 +78,8 @@ class FusedAdamW(torch.optim.Optimizer):
             steps = {self.state[p]["step"] for p, _ in plist}
             if len(steps) != 1:
                 raise RuntimeError("FusedAdamW: parameters with different step counts")
-            sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(), float(g["lr"]),
+            self._stabilise_small_grads(plist)
+            sig = tuple((p.data_ptr(), self._grad_ptr(p), self.state[p]["exp_avg"].data_ptr(), float(g["lr"]),
                          float(g["weight_decay"])) for p, g in plist)
             if sig != self._sig:          # pointers, lr (scheduler) or wd changed -> rebuild the device table
                 self._build(plist)

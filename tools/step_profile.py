@@ -21,7 +21,8 @@ cfg = dict(type='clip_vitb32', kwargs=dict(
 torch.manual_seed(0)
 model = model_entry(cfg).to(dev).train()
 crit = ClipInfoCELoss()
-opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1, fused=True)
+from declip_b200.optim import FusedAdamW  # noqa: E402
+opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1)
 images = torch.randn(b, 3, 224, 224, device=dev)
 ids = torch.zeros(b, 77, dtype=torch.long, device=dev)
 ids[:, 0] = 49407
