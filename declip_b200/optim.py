@@ -18,6 +18,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._table = None
         self._sig = None
         self._gbuf = {}      # small parameters whose autograd gradient is a fresh tensor every step (logit_scale)
+        self._last_ptr = {}
 
     def _build(self, plist):
         n = len(plist)
@@ -45,11 +46,12 @@ class FusedAdamW(torch.optim.Optimizer):
         """Gradients produced by autograd (not the towers' flat buffers) live in a new tensor each step; copying the
         small ones into persistent buffers keeps the device pointer table valid from step to step."""
         for p, _ in plist:
-            if p.numel() <= 4096:
-                buf = self._gbuf.get(p)
-                if buf is None:
-                    buf = self._gbuf[p] = torch.empty_like(p.grad)
-                buf.copy_(p.grad)
+            cur = p.grad.data_ptr()
+            if p in self._gbuf:
+                self._gbuf[p].copy_(p.grad)                      # known to move every step (e.g. logit_scale)
+            elif p.numel() <= 4096 and self._last_ptr.get(p, cur) != cur:
+                self._gbuf[p] = p.grad.detach().clone()          # moved since the last step: give it a stable home
+            self._last_ptr[p] = cur
 
     @torch.no_grad()
     def step(self, closure=None):
