@@ -64,6 +64,7 @@ SIGNATURES = {
     "dc_launch_count": (c_ll, []),
     "dc_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "dc_set_gemm_2cta": (c_int, [c_int]),
+    "dc_set_attention_tc": (None, [c_int]),
     "dc_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),
     "dc_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -175,6 +176,11 @@ def init(device_index):
         if os.environ.get("DC_GEMM_2CTA") is not None:
             lib.dc_set_gemm_2cta(int(os.environ["DC_GEMM_2CTA"] != "0"))
     return lib
+
+
+def set_attention_tc(enable):
+    """Route dc_attention_fwd/bwd to the tcgen05 core (True, default) or the mma.sync core (False)."""
+    load().dc_set_attention_tc(int(bool(enable)))
 
 
 def set_gemm_2cta(enable):

@@ -9,6 +9,7 @@
 // 128-row tcgen05 tile.  It therefore uses warp-level mma.sync.m16n8k16 (bf16 in, fp32 accumulate)
 // with ldmatrix-fed fragments; the projections around it (QKV, out-proj: 98 % of the attention
 // FLOPs) run on the tcgen05 GEMM in gemm.cu.
+#include <stdlib.h>
 #include "common.cuh"
 #include "internal.h"
 
@@ -419,12 +420,26 @@ static int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const 
 
 using namespace dc;
 
+namespace dc {
+// 1 = tcgen05 core (attention_tc.cu) whenever the shape is inside its envelope, 0 = the mma.sync core above
+static int g_attn_tc = [] {
+  const char* e = getenv("DC_ATTN_TC");
+  return (e != nullptr && e[0] == '0') ? 0 : 1;
+}();
+}  // namespace dc
+
 extern "C" {
+
+void dc_set_attention_tc(int enable) { dc::g_attn_tc = enable ? 1 : 0; }
 
 int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal,
                      dc_stream_t stream) {
   if (batch <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_attn_tc) {
+    const int rc = attention_tc_fwd(qkv, out, lse, batch, L, heads, causal, st);
+    if (rc != DC_ATTN_TC_UNSUPPORTED) return rc;
+  }
   if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");
   if (L <= 64)
     return launch_fwd<64>(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), lse, batch, L, heads, causal, st);
@@ -435,6 +450,10 @@ int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const f
                      int batch, int L, int heads, int causal, dc_stream_t stream) {
   if (batch <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_attn_tc) {
+    const int rc = attention_tc_bwd(qkv, dout, lse, dqkv, dbias, batch, L, heads, causal, st);
+    if (rc != DC_ATTN_TC_UNSUPPORTED) return rc;
+  }
   if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");
   if (L <= 64)
     return launch_bwd<64>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(out), static_cast<const bf16*>(dout), lse,

@@ -73,6 +73,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tm, uint
       : "memory");
 }
 
+// 4-D tiled load (c0 = innermost); box extents come from the tensor map, OOB elements are zero-filled.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async group); OOB rows/cols of the box are clipped by the TMA unit.
 __device__ __forceinline__ void tma_store_2d(const void* tm, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),

@@ -18,6 +18,17 @@ int sm_count();
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
                  int box_outer, int swizzle_bytes = 128);
 
+// 4-D bf16 tensor map, 128-byte swizzle: dims[0] is the contiguous extent (elements), strides_bytes[i] is the byte stride
+// of dims[i + 1]; box[0] must be 64.
+int make_tmap_4d(CUtensorMap* tm, const void* ptr, const long long dims[4], const long long strides_bytes[3],
+                 const int box[4]);
+
+// tcgen05 attention core (attention_tc.cu); return DC_ATTN_TC_UNSUPPORTED when the shape is outside its envelope
+constexpr int DC_ATTN_TC_UNSUPPORTED = -100;
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal, cudaStream_t st);
+int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias, int batch, int L,
+                     int heads, int causal, cudaStream_t st);
+
 // launchers implemented in the .cu files, used by the composite encoders
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream);
 

@@ -75,6 +75,8 @@ int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
  * previous setting.  Default 1 (measured +5-10 % over the 1-CTA 128x256 kernel, which remains the path for small
  * problems and can be forced with 0 or the DC_GEMM_2CTA=0 environment variable). */
 int dc_set_gemm_2cta(int enable);
+/* 1 (default; env DC_ATTN_TC=0 disables) = tcgen05/TMEM attention core for L <= 128, 0 = the mma.sync core (L <= 80). */
+void dc_set_attention_tc(int enable);
 
 /* ------------------------------------------------------------------ row kernels (HBM-bound)
  * LayerNorm over the last dim (eps 1e-5): base_transformer.py:10-18, visual_transformer.py:63,69,
