@@ -426,6 +426,7 @@ static int g_attn_tc = [] {
   const char* e = getenv("DC_ATTN_TC");
   return (e != nullptr && e[0] == '0') ? 0 : 1;
 }();
+bool attention_tc_enabled() { return g_attn_tc != 0; }
 }  // namespace dc
 
 extern "C" {
@@ -451,7 +452,7 @@ int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const f
   if (batch <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (g_attn_tc) {
-    const int rc = attention_tc_bwd(qkv, dout, lse, dqkv, dbias, batch, L, heads, causal, st);
+    const int rc = attention_tc_bwd(qkv, dout, lse, dqkv, dbias, /*dbias_v=*/1, batch, L, heads, causal, st);
     if (rc != DC_ATTN_TC_UNSUPPORTED) return rc;
   }
   if (L <= 0 || L > 80) return set_error("attention: sequence length must be in [1, 80]");

@@ -19,7 +19,11 @@
 // 64-thread named-barrier exchange and no shuffles.  Lane 0 of warp 0 is also the UMMA issuer and lane 0 of warp 1 the
 // TMA producer (Q, K, V, dO of the tile after next into the buffer the finished tile just released); program order of
 // the eight warps (softmax -> p_ready -> o_full -> epilogue) makes separate "empty" barriers unnecessary.  delta = rowsum(dO * O) is computed as rowsum(P * dP), so O is never read.
-// The in_proj bias gradient (column sums of dQ | dK | dV) accumulates in shared memory per head and is flushed once.
+// CTA c only ever sees head group c % (heads / pairs-per-tile), so the in_proj bias gradient needs no per-tile work:
+// its Q slice is the column sum of a dQ that the tensor core keeps accumulating over the CTA's tiles in 64 spare TMEM
+// columns, its K slice is identically zero (rows of dS sum to zero) and its V slice equals colsum(dO), which the
+// caller gets for free from the epilogue of the GEMM that produces dO (or from this kernel with db_v = 1).
+// Outputs leave through per-warp staged TMA stores (scattered 16-byte global stores made the LSU the bottleneck).
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "internal.h"
@@ -34,12 +38,14 @@ struct AttnTcParams {
   int L, heads, batch, causal;
   int pp;         // pairs per tile (1 or 2)
   int rp;         // rows per pair slot = 128 / pp
-  int num_tiles;  // batch * heads / pp
+  int groups;     // heads / pp: head groups; CTA c works on group c % groups only (one fixed head per tile slot)
+  int per_group;  // CTAs per group; CTA c takes samples b = c / groups, + per_group, ...
+  int db_v;       // backward: also produce the V slice of dbias in this kernel (external callers)
   int D;          // heads * 64
   float* lse;     // forward: out (may be null), backward: in; [batch * heads, L], natural log
   bf16* out;      // forward [batch * L, D]
   bf16* dqkv;     // backward [batch * L, 3 D]
-  float* dbias;   // backward, optional [3 D]
+  float* dbias;   // backward, optional [3 D]: Q slice always, V slice when db_v, K slice is identically zero (untouched)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -61,22 +67,48 @@ __device__ __forceinline__ void store_chunk_sw128(uint8_t* base, int row, int ch
   }
 }
 
+// One warp's 32 rows x 32 bf16 columns leave through a 2 KiB staging buffer (64-byte swizzle, conflict-free 16-byte
+// st.shared) and ONE 3-D TMA store {32 columns, 32 sequence positions, 1 sample}: positions >= L lie outside the tensor
+// and are not written, the LSU sees no scattered 16-byte global stores.  Two buffers per warp: the store issued two
+// chunks ago must have been read out, the previous one may still be in flight.
+__device__ __forceinline__ void stage_store_rows(const uint32_t (&pk)[16], uint8_t* stage, uint32_t& sidx,
+                                                 const CUtensorMap* tm, int col0, int l0, int b) {
+  const int lane = lane_id();
+  if (lane == 0) bulk_wait_read1();
+  __syncwarp();
+  stage += (sidx & 1u) * 2048;
+  sidx ^= 1u;
+  uint8_t* rowp = stage + lane * 64;
+  const int sw = (lane >> 1) & 3;    // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, stage, col0, l0, b);
+    bulk_commit();
+  }
+}
+
 template <bool BWD>
 struct AttnSmem {
   static constexpr int NIN = BWD ? 4 : 3;                        // Q, K, V (, dO)
   static constexpr uint32_t IN_BYTES = NIN * AT_TILE_BYTES;
   static constexpr uint32_t P_OFF = 2 * IN_BYTES;                // P: 2 blocks
   static constexpr uint32_t DS_OFF = P_OFF + 2 * AT_TILE_BYTES;  // dS: 2 blocks (backward)
-  static constexpr uint32_t TAIL_OFF = P_OFF + (BWD ? 4 : 2) * AT_TILE_BYTES;
-  static constexpr uint32_t XCHG_BYTES = 2 * 2 * 128 * 4;        // [which][half][row]
-  static constexpr uint32_t DB_BYTES = BWD ? AT_MAX_HEADS * 192 * 4 : 0;
+  static constexpr uint32_t STAGE_OFF = P_OFF + (BWD ? 4 : 2) * AT_TILE_BYTES;   // 8 warps x 2 x 2 KiB output staging
+  static constexpr uint32_t TAIL_OFF = STAGE_OFF + 8 * 4096;
+  static constexpr uint32_t XCHG_BYTES = (BWD ? 1 : 2) * 2 * 128 * 4;   // [which][half][row]; backward needs one
+  static constexpr uint32_t DB_BYTES = BWD ? 2 * 64 * 4 : 0;     // V-slice bias gradient per tile slot
   static constexpr uint32_t BAR_OFF = TAIL_OFF + XCHG_BYTES + DB_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + 16 * 8 + 1024;     // + alignment slack
 };
 
 template <bool BWD>
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnTcParams p) {
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+               const __grid_constant__ CUtensorMap tmOUT, const AttnTcParams p) {
   using SM = AttnSmem<BWD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -84,7 +116,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   uint8_t* sP = smem + SM::P_OFF;
   uint8_t* sdS = smem + SM::DS_OFF;
   float* xchg = reinterpret_cast<float*>(smem + SM::TAIL_OFF);  // [2][2][128]
-  float* s_db = xchg + 512;                                      // [heads][192] (backward)
+  float* s_db = xchg + 256;                                      // [2 slots][64] (backward, db_v)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
   uint64_t* ld_full = bars;        // [2]  TMA bytes of one input buffer landed
   uint64_t* s_full = bars + 2;     //      first-stage UMMAs (S [, dP]) complete
@@ -97,17 +129,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(&ld_full[0], 1); mbar_init(&ld_full[1], 1);
-    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, BWD ? 2 : 1);
     fence_mbar_init();
     prefetch_tensormap(&tmQKV);
+    prefetch_tensormap(&tmOUT);
     if (BWD) prefetch_tensormap(&tmDO);
   }
   // P / dS start as zeros: regions no warp ever writes (cross-pair blocks, fully masked causal chunks, rows >= L of
   // quadrants without work) must read as exact zeros in every tile
   for (uint32_t i = threadIdx.x; i < (BWD ? 4u : 2u) * AT_TILE_BYTES / 16; i += AT_THREADS)
     reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (BWD)
-    for (int i = threadIdx.x; i < p.heads * 192; i += AT_THREADS) s_db[i] = 0.f;
+  if (BWD && threadIdx.x < 128) s_db[threadIdx.x] = 0.f;
   fence_proxy_async_smem();
   if (warp == 0) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -120,15 +152,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const uint32_t tS = tmem_base, tdP = tmem_base + 128;
   const uint32_t tO = tmem_base + 128;                                      // forward
   const uint32_t tdQ = tmem_base + 256, tdK = tmem_base + 320, tdV = tmem_base + 384;
+  const uint32_t tdQs = tmem_base + 448;   // sum over this CTA's tiles of dQ (same head) -> Q slice of dbias
+  const int grp = blockIdx.x % p.groups;   // head group of this CTA
+  const int b0 = blockIdx.x / p.groups;    // first sample; then += per_group
 
   // ---- control helpers, each executed by ONE elected lane (warp 1: TMA producer, warp 0: UMMA issuer)
-  auto issue_loads = [&](int it, int tile) {
+  auto issue_loads = [&](int it, int b) {
     const int buf = it & 1;
     mbar_arrive_expect_tx(&ld_full[buf], SM::IN_BYTES);
     uint8_t* dst = s_in + buf * SM::IN_BYTES;
     for (int slot = 0; slot < p.pp; ++slot) {
-      const int pair = tile * p.pp + slot;
-      const int b = pair / p.heads, h = pair - b * p.heads;
+      const int h = grp * p.pp + slot;
       const uint32_t off = slot * p.rp * 128;
       tma_load_4d(dst + off, &tmQKV, &ld_full[buf], 0, h, 0, b);
       tma_load_4d(dst + AT_TILE_BYTES + off, &tmQKV, &ld_full[buf], 0, p.heads + h, 0, b);
@@ -153,12 +187,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     }
     umma_commit(s_full);
   };
-  auto issue_stage2 = [&](int it) {   // O = P V   |   dQ = dS K, dK = dS^T Q, dV = P^T dO
+  // second stage, part A (warp 0): O = P V   |   dQ = dS K and its running sum over this CTA's tiles
+  auto issue_stage2a = [&](int it) {
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
-    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);
     const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
     const uint32_t sQ = smem_u32(s_in + (it & 1) * SM::IN_BYTES);
-    const uint32_t sK = sQ + AT_TILE_BYTES, sV = sK + AT_TILE_BYTES, sdO = sV + AT_TILE_BYTES;
+    const uint32_t sK = sQ + AT_TILE_BYTES, sV = sK + AT_TILE_BYTES;
     if (!BWD) {
 #pragma unroll
       for (int s = 0; s < 8; ++s)
@@ -169,15 +203,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
       for (int s = 0; s < 8; ++s)
         umma_bf16(tdQ, umma_smem_desc(adS + (s >> 2) * AT_TILE_BYTES + (s & 3) * 32, 16, 1024),
                   umma_smem_desc(sK + s * 2048, AT_TILE_BYTES, 1024), idesc_o, s > 0);
+      if (p.dbias != nullptr) {
 #pragma unroll
-      for (int s = 0; s < 8; ++s)
-        umma_bf16(tdK, umma_smem_desc(adS + s * 2048, AT_TILE_BYTES, 1024),
-                  umma_smem_desc(sQ + s * 2048, AT_TILE_BYTES, 1024), idesc_t, s > 0);
-#pragma unroll
-      for (int s = 0; s < 8; ++s)
-        umma_bf16(tdV, umma_smem_desc(aP + s * 2048, AT_TILE_BYTES, 1024),
-                  umma_smem_desc(sdO + s * 2048, AT_TILE_BYTES, 1024), idesc_t, s > 0);
+        for (int s = 0; s < 8; ++s)
+          umma_bf16(tdQs, umma_smem_desc(adS + (s >> 2) * AT_TILE_BYTES + (s & 3) * 32, 16, 1024),
+                    umma_smem_desc(sK + s * 2048, AT_TILE_BYTES, 1024), idesc_o, (it > 0 || s > 0) ? 1u : 0u);
+      }
     }
+    umma_commit(o_full);
+  };
+  // second stage, part B (warp 2, backward only): dK = dS^T Q, dV = P^T dO
+  auto issue_stage2b = [&](int it) {
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64, true, true);
+    const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+    const uint32_t sQ = smem_u32(s_in + (it & 1) * SM::IN_BYTES);
+    const uint32_t sdO = sQ + 3 * AT_TILE_BYTES;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      umma_bf16(tdK, umma_smem_desc(adS + s * 2048, AT_TILE_BYTES, 1024),
+                umma_smem_desc(sQ + s * 2048, AT_TILE_BYTES, 1024), idesc_t, s > 0);
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      umma_bf16(tdV, umma_smem_desc(aP + s * 2048, AT_TILE_BYTES, 1024),
+                umma_smem_desc(sdO + s * 2048, AT_TILE_BYTES, 1024), idesc_t, s > 0);
     umma_commit(o_full);
   };
 
@@ -203,11 +251,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   float* xa = xchg;         // [2][128]
   float* xb = xchg + 256;   // [2][128]
 
-  auto tile_pair = [&](int tile, int& b, int& h) {
-    const int pair = tile * p.pp + slot;
-    b = pair / p.heads;
-    h = pair - b * p.heads;
-  };
+  const int h = grp * p.pp + slot;   // this thread's head (fixed for the whole kernel)
+  const int l0 = (p.pp == 2) ? (q & 1) * 32 : q * 32;   // sequence position of this warp's first row
+  const bool warp_rows = l0 < p.L;                     // any valid row in this warp?
+  uint8_t* wstage = smem + SM::STAGE_OFF + warp * 4096;
+  uint32_t sidx = 0;
   // validity bit mask of the 32 columns of a chunk for this thread's row (bit j = column j participates)
   auto chunk_mask = [&](int c) -> uint32_t {
     if (!row_valid) return 0u;
@@ -221,29 +269,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   const uint32_t mask1 = nch > 1 ? chunk_mask(ch1) : 0u;
 
   // ---- prologue: the first two tiles' loads, the first tile's first-stage UMMAs
-  const int stride = gridDim.x;
+  const int stride = p.per_group;
   if (warp == 1) {
-    if (lane == 0) {
-      if (blockIdx.x < p.num_tiles) issue_loads(0, blockIdx.x);
-      if (blockIdx.x + stride < p.num_tiles) issue_loads(1, blockIdx.x + stride);
+    if (elect_one()) {
+      if (b0 < p.batch) issue_loads(0, b0);
+      if (b0 + stride < p.batch) issue_loads(1, b0 + stride);
     }
     __syncwarp();
   }
   if (warp == 0) {
-    if (lane == 0 && blockIdx.x < p.num_tiles) issue_stage1(0);
+    if (elect_one()) {
+      if (b0 < p.batch) issue_stage1(0);
+    }
     __syncwarp();
   }
   float lse_next = 0.f;
-  if (BWD && blockIdx.x < p.num_tiles && row_valid) {
-    int b, h;
-    tile_pair(blockIdx.x, b, h);
-    lse_next = p.lse[(static_cast<size_t>(b) * p.heads + h) * p.L + l];
-  }
+  if (BWD && b0 < p.batch && row_valid) lse_next = p.lse[(static_cast<size_t>(b0) * p.heads + h) * p.L + l];
 
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += stride, ++it) {
-    int b, h;
-    tile_pair(tile, b, h);
+  for (int b = b0; b < p.batch; b += stride, ++it) {
     mbar_wait(s_full, it & 1);
     tc_fence_after();
     float m = 0.f, tot = 0.f;   // forward row statistics
@@ -346,99 +390,106 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(p_ready);
-    // ---- UMMA issuer: second stage of this tile, then the first stage of the next one (its S / dP columns are free:
-    // every warp arrived on p_ready, i.e. finished reading them, and finished the previous tile's epilogue)
+    // ---- UMMA issuers: second stage of this tile (split over two elected lanes in the backward), then the first stage
+    // of the next tile (its S / dP columns are free: every warp arrived on p_ready, i.e. finished reading them, and
+    // finished the previous tile's epilogue)
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
-        issue_stage2(it);
-        if (tile + stride < p.num_tiles) issue_stage1(it + 1);
+        issue_stage2a(it);
+        if (b + stride < p.batch) issue_stage1(it + 1);
+      }
+      __syncwarp();
+    }
+    if (BWD && warp == 2) {
+      if (elect_one()) {
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        issue_stage2b(it);
       }
       __syncwarp();
     }
     if (BWD) {
       // prefetch the next tile's log-sum-exp while the second-stage UMMAs run
-      const int nt = tile + stride;
+      const int nb = b + stride;
       lse_next = 0.f;
-      if (nt < p.num_tiles && row_valid) {
-        int nb, nh;
-        tile_pair(nt, nb, nh);
-        lse_next = p.lse[(static_cast<size_t>(nb) * p.heads + nh) * p.L + l];
-      }
+      if (nb < p.batch && row_valid) lse_next = p.lse[(static_cast<size_t>(nb) * p.heads + h) * p.L + l];
     }
     mbar_wait(o_full, it & 1);
     tc_fence_after();
     // ---- TMA producer: this tile's input buffer is free again -> fetch the tile after next into it
     if (warp == 1) {
-      if (lane == 0 && tile + 2 * stride < p.num_tiles) issue_loads(it + 2, tile + 2 * stride);
+      if (elect_one()) {
+        if (b + 2 * stride < p.batch) issue_loads(it + 2, b + 2 * stride);
+      }
       __syncwarp();
     }
     if (!BWD) {
       // ---------------------------------------------------------------- forward epilogue
-      uint32_t o[32];
-      tmem_ld32(tO + lane_base + hf * 32, o);
-      tmem_ld_wait();
-      if (row_valid) {
+      if (warp_rows) {
+        uint32_t o[32];
+        tmem_ld32(tO + lane_base + hf * 32, o);
+        tmem_ld_wait();
         const float inv = 1.0f / fmaxf(tot, 1e-30f);
-        bf16* dst = p.out + (static_cast<size_t>(b) * p.L + l) * p.D + h * 64 + hf * 32;
+        uint32_t pk[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * g) = u;
-        }
-        if (hf == 0 && p.lse != nullptr)
+        for (int j = 0; j < 16; ++j)
+          pk[j] = pack_bf16x2(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv);
+        stage_store_rows(pk, wstage, sidx, &tmOUT, h * 64 + hf * 32, l0, b);
+        if (row_valid && hf == 0 && p.lse != nullptr)
           p.lse[(static_cast<size_t>(b) * p.heads + h) * p.L + l] = (m + __log2f(fmaxf(tot, 1e-30f))) * kLn2;
       }
     } else {
       // ---------------------------------------------------------------- backward epilogue: dQ | dK | dV
-      const size_t ld = static_cast<size_t>(3) * p.D;
-      bf16* dst0 = p.dqkv + (static_cast<size_t>(b) * p.L + l) * ld + h * 64 + hf * 32;
+      if (warp_rows) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         uint32_t r[32];
         tmem_ld32((a == 0 ? tdQ : (a == 1 ? tdK : tdV)) + lane_base + hf * 32, r);
         tmem_ld_wait();
-        if (row_valid) {
-          bf16* dst = dst0 + a * p.D;
+        {
+          uint32_t pk[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
-            u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
-            u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
-            u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
-            *reinterpret_cast<uint4*>(dst + 8 * g) = u;
-          }
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          stage_store_rows(pk, wstage, sidx, &tmOUT, a * p.D + h * 64 + hf * 32, l0, b);
         }
-        if (p.dbias != nullptr) {
+        if (a == 2 && p.dbias != nullptr && p.db_v) {
           // rows >= L hold exact zeros (their P / dS rows and columns are zero), so no masking is needed
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           const float cs = chunk_colsum(v);
-          atomicAdd(&s_db[h * 192 + a * 64 + hf * 32 + lane], cs);
+          atomicAdd(&s_db[slot * 64 + hf * 32 + lane], cs);
         }
+      }
       }
     }
     tc_fence_before();   // orders this tile's tcgen05.ld before the p_ready arrive of the next tile
   }
+  if (BWD && p.dbias != nullptr && it > 0 && warp_rows) {
+    // Q slice of the in_proj bias gradient: column sums of the dQ accumulated over this CTA's tiles (all of head h);
+    // the last o_full wait above covers the accumulating UMMAs.  The K slice is identically zero (rows of dS sum to
+    // zero), the V slice is colsum(dO) — produced here only on request (db_v), else by the caller.
+    uint32_t r[32];
+    tmem_ld32(tdQs + lane_base + hf * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    const float cs = chunk_colsum(v);
+    atomicAdd(&p.dbias[h * 64 + hf * 32 + lane], cs);
+  }
+  if (lane == 0) bulk_wait_read0();   // the staging buffers must stay valid until the last stores have read them
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
-  if (BWD && p.dbias != nullptr) {
-    for (int i = threadIdx.x; i < p.heads * 192; i += AT_THREADS) {
-      const float v = s_db[i];
-      const int h = i / 192, r = i - h * 192;
-      if (v != 0.f) atomicAdd(&p.dbias[(r >> 6) * p.D + h * 64 + (r & 63)], v);
-    }
+  if (BWD && p.dbias != nullptr && p.db_v && threadIdx.x < 64 * p.pp) {
+    const int sl = threadIdx.x >> 6;
+    atomicAdd(&p.dbias[2 * p.D + (grp * p.pp + sl) * 64 + (threadIdx.x & 63)], s_db[threadIdx.x]);
   }
 }
 
@@ -447,9 +498,11 @@ static int launch_attn_tc(const void* qkv, const void* dout, AttnTcParams p, cud
   if (p.L <= 0 || p.L > 128 || p.heads > AT_MAX_HEADS) return DC_ATTN_TC_UNSUPPORTED;
   p.pp = p.L <= 64 ? 2 : 1;
   p.rp = 128 / p.pp;
-  const long long pairs = static_cast<long long>(p.batch) * p.heads;
-  if (pairs % p.pp != 0) return DC_ATTN_TC_UNSUPPORTED;
-  p.num_tiles = static_cast<int>(pairs / p.pp);
+  if (p.heads % p.pp != 0) return DC_ATTN_TC_UNSUPPORTED;
+  p.groups = p.heads / p.pp;
+  if (p.groups > sm_count()) return DC_ATTN_TC_UNSUPPORTED;
+  p.per_group = sm_count() / p.groups;
+  if (p.per_group > p.batch) p.per_group = p.batch;
   p.D = p.heads * 64;
   CUtensorMap tmQKV, tmDO;
   {
@@ -468,6 +521,18 @@ static int launch_attn_tc(const void* qkv, const void* dout, AttnTcParams p, cud
   } else {
     tmDO = tmQKV;
   }
+  CUtensorMap tmOUT;
+  {
+    // forward: out [batch * L, D]; backward: dqkv [batch * L, 3 D], as {columns, position, sample} so that a 32-row box
+    // starting inside a sample never spills into the next one
+    const long long ncol = (BWD ? 3LL : 1LL) * p.D;
+    const long long dims[3] = {ncol, p.L, p.batch};
+    const long long strides[2] = {ncol * 2, static_cast<long long>(p.L) * ncol * 2};
+    const int box[3] = {32, 32, 1};
+    int rc = make_tmap_nd(&tmOUT, BWD ? static_cast<const void*>(p.dqkv) : static_cast<const void*>(p.out), 3, dims,
+                          strides, box, 64);
+    if (rc) return rc;
+  }
   auto kern = attn_tc_kernel<BWD>;
   constexpr size_t smem = AttnSmem<BWD>::TOTAL;
   static bool set = false;
@@ -476,8 +541,8 @@ static int launch_attn_tc(const void* qkv, const void* dout, AttnTcParams p, cud
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_tc)", e);
     set = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  kern<<<grid, AT_THREADS, smem, st>>>(tmQKV, tmDO, p);
+  const int grid = p.groups * p.per_group;
+  kern<<<grid, AT_THREADS, smem, st>>>(tmQKV, tmDO, tmOUT, p);
   DC_CHECK_LAUNCH(BWD ? "attention_tc_bwd" : "attention_tc_fwd");
   return 0;
 }
@@ -489,9 +554,16 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int L, i
   return launch_attn_tc<false>(qkv, nullptr, p, st);
 }
 
-int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias, int batch, int L,
-                     int heads, int causal, cudaStream_t st) {
+bool attention_tc_supported(int batch, int L, int heads) {
+  if (batch <= 0 || L <= 0 || L > 128 || heads > AT_MAX_HEADS) return false;
+  const int pp = L <= 64 ? 2 : 1;
+  return heads % pp == 0 && heads / pp <= sm_count();
+}
+
+int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias, int dbias_v,
+                     int batch, int L, int heads, int causal, cudaStream_t st) {
   AttnTcParams p{};
+  p.db_v = dbias_v;
   p.L = L; p.heads = heads; p.batch = batch; p.causal = causal;
   p.lse = const_cast<float*>(lse); p.dqkv = static_cast<bf16*>(dqkv); p.dbias = dbias;
   return launch_attn_tc<true>(qkv, dout, p, st);

@@ -23,6 +23,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// True in exactly one (always the same) lane of a fully converged warp.  Branching on it lets ptxas keep the values
+// used inside the branch in uniform registers (no per-instruction R2UR waterfall as after `if (lane == 0)`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -85,6 +92,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tm, uint
 __device__ __forceinline__ void tma_store_2d(const void* tm, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 4-D tiled store smem -> global (bulk async group); elements outside the tensor are not written.
+__device__ __forceinline__ void tma_store_4d(const void* tm, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// 3-D tiled store smem -> global (bulk async group); elements outside the tensor are not written.
+__device__ __forceinline__ void tma_store_3d(const void* tm, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

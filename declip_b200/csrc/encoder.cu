@@ -230,9 +230,19 @@ static int layers_backward(const dc_tower_cfg& c, TowerWs& w, const void* const*
     DC_TRY(linear_wgrad(w.du, L.ln2, M, 4 * D, D, g[6], nullptr, st));
     DC_TRY(dc_layernorm_bwd(w.dtmp, L.xmid, f[4], L.mean2, L.rstd2, dx, dmid, g[10], g[11], g[3], M, D, st));
     // attention branch
-    DC_TRY(linear_dgrad(dmid, w_out, M, D, D, DC_EPI_BF16, w.dtmp, nullptr, st));     // dAttnOut
+    // in_proj_bias gradient with the tcgen05 core: Q slice from the attention kernel, V slice = colsum(dAttnOut) fused
+    // into the GEMM that produces dAttnOut, K slice identically zero
+    const bool tc = attention_tc_enabled() && attention_tc_supported(c.batch, c.seq_len, c.heads);
+    {
+      dc_gemm_args a = gemm_args(dmid, D, 0, w_out, D, 1, M, D, D, DC_EPI_BF16, w.dtmp, D);   // dAttnOut
+      if (tc) a.colsum = g[1] + 2 * D;
+      DC_TRY(gemm_bf16(a, st));
+    }
     DC_TRY(linear_wgrad(dmid, L.attn, M, D, D, g[2], nullptr, st));
-    DC_TRY(dc_attention_bwd(L.qkv, L.attn, w.dtmp, L.lse, w.dqkv, g[1], c.batch, c.seq_len, c.heads, c.causal, st));
+    if (tc)
+      DC_TRY(attention_tc_bwd(L.qkv, w.dtmp, L.lse, w.dqkv, g[1], /*dbias_v=*/0, c.batch, c.seq_len, c.heads, c.causal, st));
+    else
+      DC_TRY(dc_attention_bwd(L.qkv, L.attn, w.dtmp, L.lse, w.dqkv, g[1], c.batch, c.seq_len, c.heads, c.causal, st));
     DC_TRY(linear_dgrad(w.dqkv, w_in, M, 3 * D, D, DC_EPI_BF16, w.dtmp, nullptr, st));  // dLN1out
     DC_TRY(linear_wgrad(w.dqkv, L.ln1, M, 3 * D, D, g[0], nullptr, st));
     float* dcol_prev = (l > 0) ? grads[12 * (l - 1) + 9] : nullptr;                     // c_proj.bias of layer l-1

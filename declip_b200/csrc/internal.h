@@ -23,11 +23,19 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long ou
 int make_tmap_4d(CUtensorMap* tm, const void* ptr, const long long dims[4], const long long strides_bytes[3],
                  const int box[4]);
 
+// rank-N (2..5) bf16 tensor map; swizzle_bytes 128 (box[0] = 64 elements) or 64 (box[0] = 32 elements)
+int make_tmap_nd(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_bytes,
+                 const int* box, int swizzle_bytes);
+
 // tcgen05 attention core (attention_tc.cu); return DC_ATTN_TC_UNSUPPORTED when the shape is outside its envelope
 constexpr int DC_ATTN_TC_UNSUPPORTED = -100;
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal, cudaStream_t st);
-int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias, int batch, int L,
-                     int heads, int causal, cudaStream_t st);
+// dbias (optional, [3 D]): Q slice always; V slice only when dbias_v != 0 (it equals colsum(dout), which a caller that
+// produces dout with a GEMM gets from that GEMM's fused column sum); the K slice is identically zero and left untouched.
+int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* dqkv, float* dbias, int dbias_v,
+                     int batch, int L, int heads, int causal, cudaStream_t st);
+bool attention_tc_supported(int batch, int L, int heads);
+bool attention_tc_enabled();
 
 // launchers implemented in the .cu files, used by the composite encoders
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream);

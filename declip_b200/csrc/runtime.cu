@@ -53,28 +53,35 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long ou
   return 0;
 }
 
-int make_tmap_4d(CUtensorMap* tm, const void* ptr, const long long dims[4], const long long strides_bytes[3],
-                 const int box[4]) {
+int make_tmap_nd(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_bytes,
+                 const int* box, int swizzle_bytes) {
   if (g_encode == nullptr) return set_error("dc_init() was not called (no cuTensorMapEncodeTiled entry point)");
+  if (rank < 2 || rank > 5) return set_error("tensor map: rank must be in [2, 5]");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error("tensor map: base pointer must be 16-byte aligned");
-  cuuint64_t d[4];
-  cuuint64_t s[3];
-  cuuint32_t b[4];
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  for (int i = 0; i < 4; ++i) { d[i] = static_cast<cuuint64_t>(dims[i]); b[i] = static_cast<cuuint32_t>(box[i]); }
-  for (int i = 0; i < 3; ++i) {
+  cuuint64_t d[5];
+  cuuint64_t s[4];
+  cuuint32_t b[5];
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = static_cast<cuuint64_t>(dims[i]); b[i] = static_cast<cuuint32_t>(box[i]); }
+  for (int i = 0; i + 1 < rank; ++i) {
     if (strides_bytes[i] % 16 != 0) return set_error("tensor map: strides must be multiples of 16 bytes");
     s[i] = static_cast<cuuint64_t>(strides_bytes[i]);
   }
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), d, s, b, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), d, s,
+                        b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(4d) failed (%d): dims=%lldx%lldx%lldx%lld box=%dx%dx%dx%d",
-             static_cast<int>(r), dims[0], dims[1], dims[2], dims[3], box[0], box[1], box[2], box[3]);
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(rank %d) failed (%d): dims0=%lld box0=%d", rank,
+             static_cast<int>(r), dims[0], box[0]);
     return -2;
   }
   return 0;
+}
+
+int make_tmap_4d(CUtensorMap* tm, const void* ptr, const long long dims[4], const long long strides_bytes[3],
+                 const int box[4]) {
+  return make_tmap_nd(tm, ptr, 4, dims, strides_bytes, box, 128);
 }
 
 }  // namespace dc

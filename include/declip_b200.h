@@ -110,14 +110,18 @@ typedef struct {
 int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, float beta1,
                    float beta2, float eps, int step, dc_stream_t stream);
 
-/* ------------------------------------------------------------------ attention (L <= 80, head_dim 64)
+/* ------------------------------------------------------------------ attention (L <= 128, head_dim 64)
+ * tcgen05/TMEM core (attention_tc.cu) for L <= 128 and even head counts when L <= 64; mma.sync core (L <= 80) otherwise
+ * or after dc_set_attention_tc(0).
  * softmax(q k^T / sqrt(64) [+ causal mask]) v per (sample, head): base_transformer.py:44-48 via
  * nn.MultiheadAttention; causal mask text_transformer.py:136-142.
  * qkv bf16 [batch*L, 3*width] (q | k | v, heads contiguous inside each), out bf16 [batch*L, width],
  * lse fp32 [batch*heads*L] saved for backward. */
 int dc_attention_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal,
                      dc_stream_t stream);
-/* dbias (fp32 [3*width], may be NULL) += column sums of dqkv: the in_proj_bias gradient, fused. */
+/* dbias (fp32 [3*width], may be NULL) += column sums of dqkv: the in_proj_bias gradient, fused.  The K slice of that
+ * gradient is identically zero in exact arithmetic (every row of dS sums to zero); the tcgen05 core leaves it
+ * untouched, the mma.sync core adds its rounding noise. */
 int dc_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
                      int batch, int L, int heads, int causal, dc_stream_t stream);
 
