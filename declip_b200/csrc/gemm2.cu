@@ -132,7 +132,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
@@ -173,7 +173,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
