@@ -254,16 +254,7 @@ int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   p.total_kb = (a.K + BK - 1) / BK;
   int splits = a.splits;
   if (a.epilogue != DC_EPI_F32_ATOMIC) splits = 1;
-  if (splits <= 0) {
-    const int tiles = p.num_m * p.num_n;
-    splits = 1;
-    if (tiles < sms) {
-      splits = (2 * sms + tiles - 1) / tiles;
-      const int max_splits = (p.total_kb + 3) / 4;  // at least 4 k-blocks per split
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
-    }
-  }
+  if (splits <= 0) splits = choose_splits(p.num_m * p.num_n, p.total_kb, sms);
   if (splits > p.total_kb) splits = p.total_kb;
   p.kb_per_split = (p.total_kb + splits - 1) / splits;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;

@@ -284,16 +284,7 @@ int gemm2_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   const int clusters_max = sms / 2;
   int splits = a.splits;
   if (a.epilogue != DC_EPI_F32_ATOMIC) splits = 1;
-  if (splits <= 0) {
-    const int tiles = p.num_m * p.num_n;
-    splits = 1;
-    if (tiles < clusters_max) {
-      splits = (2 * clusters_max + tiles - 1) / tiles;
-      const int max_splits = (p.total_kb + 3) / 4;
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
-    }
-  }
+  if (splits <= 0) splits = choose_splits(p.num_m * p.num_n, p.total_kb, clusters_max);
   if (splits > p.total_kb) splits = p.total_kb;
   p.kb_per_split = (p.total_kb + splits - 1) / splits;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;

@@ -37,6 +37,25 @@ int attention_tc_bwd(const void* qkv, const void* dout, const float* lse, void* 
 bool attention_tc_supported(int batch, int L, int heads);
 bool attention_tc_enabled();
 
+// Split-K factor for an fp32-atomic GEMM of `tiles` output tiles and `total_kb` k-blocks on `workers` persistent CTAs
+// (clusters): minimises waves x (k-blocks per split + per-item overhead) — `tiles * splits` just above a multiple of
+// `workers` costs a whole extra wave, which a fill-the-machine-twice rule hits for most weight-gradient shapes.
+inline int choose_splits(int tiles, int total_kb, int workers) {
+  if (tiles >= workers) return 1;
+  int max_splits = (total_kb + 3) / 4;          // at least 4 k-blocks per split
+  if (max_splits > 64) max_splits = 64;
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= max_splits; ++s) {
+    const int kbps = (total_kb + s - 1) / s;
+    const int eff = (total_kb + kbps - 1) / kbps;                 // splits that actually get work
+    const long long waves = (static_cast<long long>(tiles) * eff + workers - 1) / workers;
+    const long long cost = waves * (kbps + 3);                   // +3: pipeline fill / accumulator hand-off per item
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 // launchers implemented in the .cu files, used by the composite encoders
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream);
 
