@@ -223,6 +223,15 @@ __global__ void bn2d_finalize_kernel(const float* __restrict__ sums, float* __re
   }
 }
 
+// eval mode: statistics come from the running buffers (nn.BatchNorm2d.eval())
+__global__ void bn2d_eval_stats_kernel(const float* __restrict__ run_mean, const float* __restrict__ run_var,
+                                       float* __restrict__ mean, float* __restrict__ rstd, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = run_mean[c];
+  rstd[c] = rsqrtf(run_var[c] + eps);
+}
+
 // y = [relu]( (x - mean) * rstd * gamma + beta [+ res] )
 __global__ void __launch_bounds__(256) bn2d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -427,7 +436,9 @@ int dc_bn2d_fwd(const void* x, const float* gamma, const float* beta, const void
                                                           static_cast<double>(rows), C, eps, momentum);
     DC_CHECK_LAUNCH("bn2d_finalize");
   } else {
-    return set_error("bn2d: eval mode (running statistics) is not built for the NHWC path yet");
+    if (running_mean == nullptr || running_var == nullptr) return set_error("bn2d: eval mode needs the running statistics");
+    bn2d_eval_stats_kernel<<<(C + 255) / 256, 256, 0, st>>>(running_mean, running_var, mean, rstd, C, eps);
+    DC_CHECK_LAUNCH("bn2d_eval_stats");
   }
   bn2d_apply_kernel<<<grid_for_items(static_cast<size_t>(rows) * (C / 8), 256), 256, 0, st>>>(
       static_cast<const bf16*>(x), mean, rstd, gamma, beta, static_cast<const bf16*>(res), static_cast<bf16*>(y),

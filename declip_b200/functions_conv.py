@@ -107,7 +107,7 @@ class BatchNorm2dNHWC(torch.autograd.Function):
     reference's shim) fused with the optional residual add and ReLU (modified_resnet.py:40-56)."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, running_mean, running_var, relu, eps, momentum):
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, relu, eps, momentum, training=True):
         lib = ops.lib_for(x)
         rows, C = x.shape
         y = torch.empty_like(x)
@@ -115,14 +115,17 @@ class BatchNorm2dNHWC(torch.autograd.Function):
         rstd = torch.empty(C, device=x.device, dtype=torch.float32)
         scratch = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         _lib.check(lib.dc_bn2d_fwd(_p(x), _p(gamma), _p(beta), _p(res), _p(y), _p(mean), _p(rstd), _p(running_mean),
-                                   _p(running_var), _p(scratch), rows, C, float(eps), float(momentum), 1, int(relu),
-                                   _stream()), "dc_bn2d_fwd")
+                                   _p(running_var), _p(scratch), rows, C, float(eps), float(momentum), int(bool(training)),
+                                   int(relu), _stream()), "dc_bn2d_fwd")
+        ctx.bn_training = bool(training)
         ctx.save_for_backward(x, y, gamma, mean, rstd)
         ctx.relu, ctx.has_res = bool(relu), res is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        if not ctx.bn_training:
+            raise NotImplementedError("declip_b200: backward through eval-mode BatchNorm2d (frozen statistics) is not built")
         x, y, gamma, mean, rstd = ctx.saved_tensors
         lib = ops.lib_for(x)
         rows, C = x.shape
@@ -134,7 +137,7 @@ class BatchNorm2dNHWC(torch.autograd.Function):
         scratch = torch.empty(2 * C, device=x.device, dtype=torch.float32)
         _lib.check(lib.dc_bn2d_bwd(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(rstd), _p(dx), _p(dres), _p(dg), _p(db),
                                    _p(scratch), rows, C, int(ctx.relu), _stream()), "dc_bn2d_bwd")
-        return dx, dres, dg, db, None, None, None, None, None
+        return dx, dres, dg, db, None, None, None, None, None, None
 
 
 class AvgPool2(torch.autograd.Function):

@@ -16,8 +16,9 @@ from .. import functions_conv as C_
 
 
 def _bn(bn, x, res=None, relu=True):
-    if not bn.training:
-        raise NotImplementedError("declip_b200: ModifiedResNet eval-mode BatchNorm (running statistics) is not built yet")
+    if not bn.training:     # model.eval(): running statistics (zero-shot evaluation, clip_solver.py:675-737)
+        return C_.BatchNorm2dNHWC.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, relu, bn.eps,
+                                        bn.momentum, False)
     if bn.track_running_stats:
         bn.num_batches_tracked += 1
     return C_.BatchNorm2dNHWC.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, relu, bn.eps, bn.momentum)
