@@ -99,6 +99,12 @@ SIGNATURES = {
     "dc_gather_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_dot_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "dc_bpe_create": (c_void_p, [ctypes.c_char_p, c_ll]),
+    "dc_bpe_destroy": (None, [c_void_p]),
+    "dc_bpe_vocab_size": (c_int, [c_void_p]),
+    "dc_bpe_token_id": (c_int, [c_void_p, ctypes.c_char_p]),
+    "dc_bpe_encode": (c_ll, [c_void_p, ctypes.c_char_p, c_void_p, c_ll]),
+    "dc_bpe_tokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),

@@ -5,6 +5,8 @@ tokenizer is available) or — the fast path every benchmark and test uses — a
 [B, 77] (SOT ... EOT, zero padded).  HF BERT/GPT2/Roberta branches are out of scope (hard-coded cluster
 paths, text_transformer.py:51-102).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -28,6 +30,9 @@ class TextTransformer(nn.Module):
         self.text_model_utils = text_model_utils or {}
         self.tokenizer = None
         self.bpe_path = bpe_path
+        if bpe_path is not None and os.path.exists(str(bpe_path)):
+            from ..tokenizer import SimpleTokenizer            # C++ BPE (csrc/bpe.cu), text_transformer.py:35-36
+            self.tokenizer = SimpleTokenizer(bpe_path)
         self.transformer = Transformer(width=transformer_width, layers=transformer_layers, heads=transformer_heads,
                                        attn_mask=self.build_attention_mask(), checkpoint=checkpoint)
         self.vocab_size = VOCAB_SIZE
@@ -69,16 +74,11 @@ class TextTransformer(nn.Module):
         if self.tokenizer is None:
             raise RuntimeError("declip_b200: no BPE tokenizer loaded (bpe_path=%r). Pass a pre-tokenised LongTensor "
                                "[B,%d] instead of strings." % (self.bpe_path, self.context_length))
-        if isinstance(texts, str):
-            texts = [texts]
-        sot, eot = self.tokenizer.encoder["<|startoftext|>"], self.tokenizer.encoder["<|endoftext|>"]
-        result = torch.zeros(len(texts), context_length, dtype=torch.long)
-        for i, text in enumerate(texts):
-            tokens = [sot] + self.tokenizer.encode(text) + [eot]
-            if len(tokens) > context_length:
-                tokens = [tokens[0]] + tokens[1:context_length - 1] + [tokens[-1]]
-            result[i, :len(tokens)] = torch.tensor(tokens, dtype=torch.long)
-        return result
+        if mask_type is not None:
+            ids = self.tokenizer.tokenize(texts, context_length)
+            from .text_utils import mask_tokens_batch
+            return mask_tokens_batch(ids)
+        return self.tokenizer.tokenize(texts, context_length, return_length=return_length)
 
     def forward(self, text, mask_type=None, return_dense=False):
         """text: List[str] (reference API) | LongTensor ids [B,77] | (masked_ids, labels) when already MLM-masked.

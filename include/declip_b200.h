@@ -234,6 +234,24 @@ int dc_add_bf16(const void* a, const void* b, void* out, size_t n, dc_stream_t s
 int dc_attnpool_assemble(const void* x, const float* pos, void* tokens, int batch, int P, int C, dc_stream_t stream);
 int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, int C, dc_stream_t stream);
 
+/* ------------------------------------------------------------------ host-side text front end (no device work)
+ * Byte-pair-encoding tokenizer = prototype/model/utils/text_utils/simple_tokenizer.py:66-134 (OpenAI CLIP BPE plus the
+ * extra <|mask|> token: vocabulary = merges + 515) and the truncation / zero padding of TextTransformer.tokenize
+ * (text_encoder/text_transformer.py:144-170).  `merges_text` is the DECOMPRESSED content of
+ * bpe_simple_vocab_16e6.txt.gz.  Texts are NUL-terminated UTF-8, already cleaned and lower-cased by the caller
+ * (simple_tokenizer.py:53-63,126).  Thread-safe; dc_bpe_tokenize splits the batch over `threads` host threads. */
+typedef struct dc_bpe dc_bpe_t;
+dc_bpe_t* dc_bpe_create(const char* merges_text, long long nbytes);      /* NULL on error (dc_last_error) */
+void dc_bpe_destroy(dc_bpe_t* h);
+int dc_bpe_vocab_size(const dc_bpe_t* h);
+int dc_bpe_token_id(const dc_bpe_t* h, const char* token);              /* e.g. "<|endoftext|>"; -1 if absent */
+/* ids of ONE text without SOT / EOT; returns the token count (may exceed `capacity`; only that many are written), < 0 on error */
+long long dc_bpe_encode(dc_bpe_t* h, const char* text, int* ids_out, long long capacity);
+/* ids[n, context_length] (int64) = SOT + tokens + EOT, truncated to SOT + first context_length-2 tokens + EOT, zero
+ * padded; lengths[n] (optional) = tokens written per row. */
+int dc_bpe_tokenize(dc_bpe_t* h, const char* const* texts, int n, int context_length, long long* ids, int* lengths,
+                    int threads);
+
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.
  * Weight/grad tables are arrays of device pointers in the order documented in encoder.h order
