@@ -329,10 +329,10 @@ def run_native(args):
         kms = s.elapsed_time(e) / iters
         ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # DRAM bytes of this launch shape from the ncu --set full capture (profiles/r01_ncu_gemm_gelu_v1.md:
-                # dram read 48.2 MB + write 263.6 MB at b=512; algorithmic 44.0 + 314.6 MB, part of the output is still
+                # DRAM bytes of this launch shape from the ncu --set full capture (profiles/r01_ncu_gemm_gelu_v7.md:
+                # dram read 44.3 MB + write 260.3 MB at b=512; algorithmic 44.0 + 314.6 MB, part of the output is still
                 # in L2 at kernel end) scaled to the batch in use
-                "traffic": 311.8e6 * (b / 512.0),
+                "traffic": 304.6e6 * (b / 512.0),
                 "kernel": "gemm2_bf16_kernel<K-major,K-major> (cta_group::2) c_fc+QuickGELU fwd M=%d N=%d K=%d" % (M, N, K),
                 "kernel_ms": kms, "peak_source": which,
                 "step_mfu": {"achieved_tflops_per_gpu": b * args.steps / (ms / 1e3) * TRAIN_GFLOP_PER_PAIR / 1e3,
