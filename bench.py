@@ -38,6 +38,11 @@ def log(msg):
         print("[bench %.1fs] %s" % (time.time() - _T0, msg), file=sys.stderr, flush=True)
 
 
+# NCCL prints "NCCL version ..." on STDOUT when NCCL_DEBUG=VERSION (set in some images): keep stdout to the one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
