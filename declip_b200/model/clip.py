@@ -56,8 +56,11 @@ class CLIP(nn.Module):
     def forward(self, input, all_gather=False):
         images = input['images']
         texts = self._texts(input)
-        image_features = self.encode_image(images)
+        # The text tower runs first so that autograd (latest node first) runs the IMAGE tower's backward first: its
+        # gradient all-reduce — the larger bucket — is then hidden behind the text tower's backward (dist.py).
+        # The reference encodes the image first (clip.py:126-127); the two towers are independent, the results identical.
         text_features = self.encode_text(texts)
+        image_features = self.encode_image(images)
         gather = (self.training and self.use_allgather) or all_gather             # clip.py:136
         logits_per_image, logits_per_text = F_.ClipLogits.apply(image_features, text_features, self.logit_scale,
                                                                 gather, True)
