@@ -155,6 +155,40 @@ def test_attention(cuda_dev, L, H, causal):
     assert _rel(dbias - 1, qr.grad.sum(0)) < 2e-2                      # fused in_proj_bias gradient
 
 
+@pytest.mark.parametrize("B,L,H,causal", [(6, 50, 12, 0), (3, 77, 8, 1), (2, 128, 2, 1), (4, 50, 32, 0), (3, 17, 2, 0),
+                                          (150, 50, 12, 0), (3, 50, 3, 0)])
+def test_attention_tcgen05_core_against_fp32_and_the_mma_core(cuda_dev, B, L, H, causal):
+    """The tcgen05 core (default) and the mma.sync core (fallback; also taken for odd head counts at L <= 64) against
+    the fp32 restatement, at tile-boundary shapes: two pairs per tile (L <= 64), one pair (L > 64), L = 128 (full
+    tile), more tiles than CTAs (B = 150), and a shape outside the tcgen05 envelope (3 heads at L = 50)."""
+    from declip_b200 import _lib, ops
+    torch.manual_seed(11)
+    D = H * 64
+    qkv = (torch.randn(B * L, 3 * D, device=cuda_dev) * 1.5).bfloat16()
+    dout = torch.randn(B * L, D, device=cuda_dev).bfloat16()
+    qr = qkv.float().requires_grad_(True)
+    o_ref, lse_ref = _ref_attention(qr, B, L, H, causal)
+    o_ref.backward(dout.float())
+    try:
+        for tc in (True, False):
+            if not tc and L > 80:
+                continue
+            _lib.set_attention_tc(tc)
+            out, lse = ops.attention_fwd(qkv, B, L, H, causal)
+            dbias = torch.zeros(3 * D, device=cuda_dev)
+            dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, causal, dbias=dbias)
+            assert _cos(out, o_ref) > 0.9999 and torch.allclose(lse.view(B, H, L), lse_ref, atol=2e-3), tc
+            assert _cos(dqkv, qr.grad) > 0.9995 and torch.isfinite(dqkv.float()).all(), tc
+            ref_b = qr.grad.sum(0)
+            # Q and V slices of the in_proj bias gradient; the K slice is zero in exact arithmetic (rounding noise in
+            # both the reference and the kernels)
+            for sl in (slice(0, D), slice(2 * D, 3 * D)):
+                assert _cos(dbias[sl], ref_b[sl]) > 0.999, tc
+            assert dbias[D:2 * D].abs().max() < 0.05 * dbias.abs().max(), tc
+    finally:
+        _lib.set_attention_tc(True)
+
+
 def test_embeddings(cuda_dev):
     from declip_b200 import ops
     torch.manual_seed(4)
