@@ -31,6 +31,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in
+// the stream is still draining: everything up to pdl_wait() (barrier init, TMEM allocation, tensor-map prefetch) then
+// overlaps the predecessor's last wave.  pdl_wait() returns once the predecessor grid has completed and its memory is
+// visible; pdl_launch_dependents() lets the successor start its own prologue as soon as this grid's CTAs retire.
+// Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -86,6 +86,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();
 
   const int tiles_mn = p.num_m * p.num_n;
 
@@ -223,8 +225,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm)", e);
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmO, tmO2, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm launch", e);
   count_launch();
   return 0;

@@ -127,6 +127,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   cluster_sync_all();   // barriers of both CTAs initialised and TMEM allocated before any remote traffic
   tc_fence_after();
+  pdl_wait();                 // everything above overlaps the tail of the previous kernel in the stream
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int tiles_mn = p.num_m * p.num_n;   // num_m counts 256-row tiles here
 
@@ -265,8 +267,8 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(gemm2)", e);
     attr_set = true;
   }
-  kern<<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(tmA, tmB, tmO, tmO2, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(kern, dim3(2 * clusters), dim3(GEMM_THREADS), G2_SMEM_BYTES, stream, tmA, tmB, tmO, tmO2, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error_cuda("gemm2 launch", e);
   count_launch();
   return 0;

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 #include "../../include/declip_b200.h"
 
 namespace dc {
@@ -54,6 +55,20 @@ inline int choose_splits(int tiles, int total_kb, int workers) {
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
   return best;
+}
+
+// Launches `kern` with programmatic stream serialization (see common.cuh: pdl_wait) unless DC_PDL=0.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // launchers implemented in the .cu files, used by the composite encoders

@@ -5,6 +5,7 @@
 #include <string.h>
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include "internal.h"
 
 namespace dc {
@@ -51,6 +52,11 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long ou
     return -2;
   }
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DC_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
 }
 
 int make_tmap_nd(CUtensorMap* tm, const void* ptr, int rank, const long long* dims, const long long* strides_bytes,
