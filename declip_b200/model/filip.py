@@ -14,6 +14,26 @@ from .visual_transformer import visual_transformer_B32
 __all__ = ['filip_vitb32', 'filip_res50', 'FILIP']
 
 
+def weighted_dense_logits(dense_feat_1, dense_feat_2, logit_scale_dense, top_k=16):
+    """Token-wise late interaction with top-k token selection (filip.py:71-106, defilip.py:223-267): unit-norm tokens,
+    the top_k tokens of each side by summed cross similarity are all-gathered, every local token takes its best match
+    among the selected tokens of every sample, averaged over the local tokens.  dense_feat_* fp32 [B, n, dim]."""
+    B, n1, dim = dense_feat_1.shape
+    n2 = dense_feat_2.shape[1]
+    d1 = F_.L2Normalize.apply(dense_feat_1.reshape(B * n1, dim), 0.0)
+    d2 = F_.L2Normalize.apply(dense_feat_2.reshape(B * n2, dim), 0.0)
+    s1, s2 = F_.token_scores(d1.detach(), d2.detach(), B, n1, n2)
+    id1 = torch.topk(s1, k=top_k, dim=1).indices + torch.arange(B, device=s1.device)[:, None] * n1
+    id2 = torch.topk(s2, k=top_k, dim=1).indices + torch.arange(B, device=s1.device)[:, None] * n2
+    sel1 = F_.GatherRowsF32.apply(d1, id1.reshape(-1).to(torch.int32))                     # [B*k, dim]
+    sel2 = F_.GatherRowsF32.apply(d2, id2.reshape(-1).to(torch.int32))
+    sel1 = F_.AllGatherRows.apply(sel1)
+    sel2 = F_.AllGatherRows.apply(sel2)
+    l1 = F_.FilipLate.apply(d1, sel2, logit_scale_dense, n1, top_k)
+    l2 = F_.FilipLate.apply(d2, sel1, logit_scale_dense, n2, top_k)
+    return l1, l2
+
+
 class FILIP(CLIP):
     def __init__(self, image_encode, text_encode, use_allgather, nn_size=2 ** 16, nn_topk=1, return_dense=False,
                  return_caption=False, return_nn_bank=False, text_mask_type=None, EDA=True, feature_dim=1024,
@@ -44,20 +64,7 @@ class FILIP(CLIP):
         if not self.select_topk:
             raise NotImplementedError("declip_b200: FILIP without select_topk is a latent bug in the reference "
                                       "(selected_feat undefined, filip.py:90-94)")
-        B, n1, dim = dense_feat_1.shape
-        n2 = dense_feat_2.shape[1]
-        d1 = F_.L2Normalize.apply(dense_feat_1.reshape(B * n1, dim), 0.0)                      # filip.py:72-73
-        d2 = F_.L2Normalize.apply(dense_feat_2.reshape(B * n2, dim), 0.0)
-        s1, s2 = F_.token_scores(d1.detach(), d2.detach(), B, n1, n2)                          # filip.py:79-81
-        id1 = torch.topk(s1, k=top_k, dim=1).indices + torch.arange(B, device=s1.device)[:, None] * n1
-        id2 = torch.topk(s2, k=top_k, dim=1).indices + torch.arange(B, device=s1.device)[:, None] * n2
-        sel1 = F_.GatherRowsF32.apply(d1, id1.reshape(-1).to(torch.int32))                     # [B*k, dim]  :83-88
-        sel2 = F_.GatherRowsF32.apply(d2, id2.reshape(-1).to(torch.int32))
-        sel1 = F_.AllGatherRows.apply(sel1)                                                    # :93-94
-        sel2 = F_.AllGatherRows.apply(sel2)
-        l1 = F_.FilipLate.apply(d1, sel2, self.logit_scale_dense, n1, top_k)                   # :103
-        l2 = F_.FilipLate.apply(d2, sel1, self.logit_scale_dense, n2, top_k)                   # :104
-        return l1, l2
+        return weighted_dense_logits(dense_feat_1, dense_feat_2, self.logit_scale_dense, top_k)
 
     def forward(self, input, return_dict=False):
         if not return_dict:

@@ -130,3 +130,20 @@ def declip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_by_size):
     return {"loss": loss.detach(), "parts": {k: v.detach() for k, v in parts.items()}, "out": out,
             "grads": {k: p.grad for k, p in params.items() if p.grad is not None}, "stats": stats,
             "bank": bank.bank, "bank_ptr": bank.ptr}
+
+
+# yfcc15m_vit_defilip/config.yaml: the DeCLIP weights plus `filip: 0.2` (defilip_solver.py:462-480,541-542)
+DEFILIP_FILIP_WEIGHT = 0.2
+
+
+def defilip_loss(out, weights=LOSS_WEIGHTS, filip_weight=DEFILIP_FILIP_WEIGHT, world=1):
+    """declip_loss + the FILIP term: mean of the (up to four) dense InfoNCE losses."""
+    ce = lambda a, b: clip_ref.clip_info_ce(a, b)[0]
+    loss, parts = declip_loss(out, weights, world)
+    f = ce(*out["filip"])
+    if "filip_aug" in out:
+        a = out["filip_aug"]
+        f = (f + ce(a[0], a[1]) + ce(a[2], a[3]) + ce(a[4], a[5])) / 4
+    f = f / world
+    parts = dict(parts, filip=f)
+    return loss + f * filip_weight, parts

@@ -16,6 +16,21 @@ DECLIP_CASES = {
 }
 
 
+DEFILIP_CASES = {
+    # DeCLIP batch + token-wise late interaction on all four (view, caption) combinations (return_filip, dense_aug)
+    "defilip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=7, nn_size=1024),
+}
+
+
+def defilip_inputs(c):
+    from . import synth
+    sd, images, mlm_ids, mlm_labels, ids_aug, bank = declip_inputs(c)
+    extra = synth.filip_extra_state_dict(seed=c["seed"])
+    for k in ("logit_scale_dense", "image_mapping.weight", "image_mapping.bias", "text_mapping.weight", "text_mapping.bias"):
+        sd[k] = extra[k]
+    return sd, images, mlm_ids, mlm_labels, ids_aug, bank
+
+
 FILIP_CASES = {
     "filip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=768, seed=4),
 }

@@ -150,6 +150,39 @@ def reference_declip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_by
     return res, model
 
 
+def reference_defilip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_by_size, embed_dim=512, v_layers=12,
+                           t_layers=12):
+    """Reference defilip_vitb32 (DeCLIP heads + return_filip + dense_aug) forward, the solver's loss composition
+    (defilip_solver.py:435-545 restated by oracle.declip_ref.defilip_loss on the reference's OWN outputs), backward."""
+    setup()
+    _ensure_pg()
+    from prototype.model import model_entry
+    from . import declip_ref
+    nn_size = bank_dim_by_size.shape[1]
+    cfg = dict(type="defilip_vitb32", kwargs=dict(
+        image_encode=dict(embed_dim=embed_dim, layers=v_layers),
+        text_encode=dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=embed_dim, transformer_layers=t_layers),
+        clip=dict(use_allgather=True, text_mask_type="MLM", return_nn_bank=True, feature_dim=embed_dim, nn_size=nn_size,
+                  return_filip=True, dense_aug=True)))
+    model = model_entry(cfg).train()
+    model.load_state_dict(sd, strict=True)
+    model.nn_replacer_text.bank = bank_dim_by_size.clone()
+    model.nn_replacer_text.bank_ptr = torch.LongTensor([0])
+
+    def _tok(texts, context_length=77, return_length=False, mask_type=None):
+        return (mlm_ids.clone(), mlm_labels.clone()) if mask_type is not None else ids_aug
+    model.encode_text.tokenize = _tok
+    B = images6.shape[0]
+    out = model({"images": images6, "captions": [["x"]] * B}, return_dict=True)
+    loss, parts = declip_ref.defilip_loss(out)
+    loss.backward()
+    return {"loss": loss.detach(), "parts": {k: v.detach() for k, v in parts.items()}, "out": out,
+            "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None},
+            "stats": {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k},
+            "bank": model.nn_replacer_text.bank.clone(), "bank_ptr": int(model.nn_replacer_text.bank_ptr)}, model
+
+
 def reference_filip_step(sd, images6, mlm_ids, mlm_labels, embed_dim=768, v_layers=12, t_layers=12, weights=None):
     """Reference filip_vitb32 (return_dense, select_topk, MLM tokenisation) forward + the solver's loss + backward."""
     setup()
