@@ -110,6 +110,9 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "dc_vit_backward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
+    "dc_tower_pre_features": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p]),
+    "dc_vit_backward_pre": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
     "dc_token_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dc_groupmax_mean_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "dc_groupmax_mean_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

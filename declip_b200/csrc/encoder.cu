@@ -316,8 +316,24 @@ int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sampl
   return gemm_bf16(a, st);
 }
 
+int dc_tower_pre_features(const dc_tower_cfg* cfg, const void* workspace, void* out_bf16, dc_stream_t stream) {
+  DC_TRY(check_cfg(cfg));
+  TowerWs w;
+  carve(*cfg, const_cast<void*>(workspace), w);
+  cudaError_t e = cudaMemcpyAsync(out_bf16, w.rows_ln, static_cast<size_t>(cfg->batch) * cfg->width * sizeof(bf16),
+                                  cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return set_error_cuda("tower_pre_features", e);
+  return 0;
+}
+
 int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* ddense, const void* const* w_bf16,
                     const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream) {
+  return dc_vit_backward_pre(cfg, dfeatures, nullptr, ddense, w_bf16, w_f32, grads, workspace, stream);
+}
+
+int dc_vit_backward_pre(const dc_tower_cfg* cfg, const float* dfeatures, const void* dpre, const void* ddense,
+                        const void* const* w_bf16, const float* const* w_f32, float* const* grads, void* workspace,
+                        dc_stream_t stream) {
   DC_TRY(check_cfg(cfg));
   const dc_tower_cfg& c = *cfg;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -333,9 +349,11 @@ int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void*
     dc_gemm_args a = gemm_args(w.rows_ln, D, 1, w.dfeat, E, 1, D, E, c.batch, DC_EPI_F32_ATOMIC, xg[6], E);
     DC_TRY(gemm_bf16(a, st));
   }
-  // d rows_ln[b,D] = dfeat[b,E] proj[D,E]^T
+  // d rows_ln[b,D] = dfeat[b,E] proj[D,E]^T  (+ the gradient of the pre-projection feature when it was handed out)
   {
-    dc_gemm_args a = gemm_args(w.dfeat, E, 0, proj, E, 0, c.batch, D, E, DC_EPI_BF16, w.drow, D);
+    dc_gemm_args a = gemm_args(w.dfeat, E, 0, proj, E, 0, c.batch, D, E, dpre != nullptr ? DC_EPI_BF16_RESID : DC_EPI_BF16,
+                               w.drow, D);
+    a.aux = dpre; a.ldaux = D;
     DC_TRY(gemm_bf16(a, st));
   }
   DC_TRY(dc_layernorm_bwd(w.drow, w.rows, xf[4], w.mean_post, w.rstd_post, nullptr, w.drow2, xg[4], xg[5],

@@ -10,15 +10,16 @@ from .clip import CLIP, clip_res50, clip_vitb32  # noqa: F401
 from .declip import DECLIP, declip_res50, declip_vitb32  # noqa: F401
 from .defilip import DEFILIP, defilip_vitb32  # noqa: F401
 from .filip import FILIP, filip_res50, filip_vitb32  # noqa: F401
+from .slip import SLIP, slip_vitb32  # noqa: F401
 
-_NOT_BUILT = ('slip_res50', 'slip_vitb32')
+_NOT_BUILT = ('slip_res50',)
 
 
 def model_entry(config):
     name = config['type']
     if name in _NOT_BUILT:
-        raise NotImplementedError("declip_b200: model type %r is not built (SLIP needs the pre-projection feature of the "
-                                  "image tower, SURVEY.md §8f rank 4)" % name)
+        raise NotImplementedError("declip_b200: model type %r cannot run in the reference either (ModifiedResNet.forward "
+                                  "has no return_feature argument, modified_resnet.py:192)" % name)
     if name not in globals():
         raise KeyError("unknown model type %r" % name)
     return globals()[name](**config['kwargs'])

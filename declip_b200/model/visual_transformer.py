@@ -55,16 +55,16 @@ class VisualTransformer(nn.Module):
         return self
 
     def forward(self, x, return_dense=False, return_feature=False):
-        if return_feature:
-            raise NotImplementedError("declip_b200: return_feature (pre-projection class feature) is unused by the "
-                                      "reference wrappers")
+        """visual_transformer.py:55-82: x [, dense_feat] [, feature] — `feature` is ln_post(class token) before `proj`."""
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError("expected images [B,3,%d,%d], got %s" % (self.input_resolution, self.input_resolution,
                                                                       tuple(x.shape)))
-        if return_dense:   # (x, dense_feat) with dense_feat = last-block patch tokens, bf16 [B, 49, width]
-            feats, dense = run_tower(self._rt, x, dense=True)
-            return feats, dense.view(x.shape[0], self._rt.seq_len - 1, -1)
-        return run_tower(self._rt, x)
+        if not (return_dense or return_feature):
+            return run_tower(self._rt, x)
+        out = list(run_tower(self._rt, x, dense=return_dense, pre=return_feature))
+        if return_dense:   # dense_feat = last-block patch tokens, bf16 [B, 49, width]
+            out[1] = out[1].view(x.shape[0], self._rt.seq_len - 1, -1)
+        return tuple(out)
 
 
 def visual_transformer_B32(**kwargs):

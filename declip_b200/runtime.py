@@ -130,6 +130,13 @@ class TowerRuntime:
         return torch.empty(nbytes, device=dev, dtype=torch.uint8)
 
     # ------------------------------------------------------------------ executors
+    def pre_features(self, cfg, ws):
+        """bf16 [batch, width]: the pre-projection feature of the forward that filled `ws` (dc_tower_pre_features)."""
+        out = torch.empty(cfg.batch, self.width, device=ws.device, dtype=torch.bfloat16)
+        _lib.check(self.lib.dc_tower_pre_features(ctypes.byref(cfg), _PTR(ws.data_ptr()), _PTR(out.data_ptr()), _stream()),
+                   "dc_tower_pre_features")
+        return out
+
     def forward(self, inp, params, dense=False):
         self._prepare(params)
         self.refresh_shadows(params)
@@ -161,7 +168,7 @@ class TowerRuntime:
             return feats, inp, cfg, ws, words
         return feats, inp, cfg, ws, None
 
-    def backward(self, cfg, inp, ws, dfeats, params, dense=False, dwords=None):
+    def backward(self, cfg, inp, ws, dfeats, params, dense=False, dwords=None, dpre=None):
         """Accumulates parameter gradients straight into `p.grad` (views of one flat fp32 buffer per tower, the
         DDP/"main_grad" pattern), so the gradient all-reduce is a single NCCL call per tower and a module that is
         run several times per step accumulates correctly.  Ownership rules per parameter:
@@ -202,9 +209,12 @@ class TowerRuntime:
         if dwords is not None:
             dwords = dwords.to(torch.bfloat16).contiguous()
         if self.kind == "vit":
-            _lib.check(self.lib.dc_vit_backward(ctypes.byref(cfg), _PTR(dfeats.data_ptr()),
-                                                _PTR(dwords.data_ptr()) if dwords is not None else None, self.w_bf16,
-                                                self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
+            if dpre is not None:
+                dpre = dpre.to(torch.bfloat16).contiguous()
+            _lib.check(self.lib.dc_vit_backward_pre(ctypes.byref(cfg), _PTR(dfeats.data_ptr()),
+                                                    _PTR(dpre.data_ptr()) if dpre is not None else None,
+                                                    _PTR(dwords.data_ptr()) if dwords is not None else None, self.w_bf16,
+                                                    self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()), "dc_vit_backward")
         else:
             _lib.check(self.lib.dc_text_backward(ctypes.byref(cfg), _PTR(inp.data_ptr()), _PTR(dfeats.data_ptr()),
                                                  int(dense), _PTR(dwords.data_ptr()) if dwords is not None else None,
@@ -232,34 +242,45 @@ class _TowerFunction(torch.autograd.Function):
     written into p.grad by the runtime (see TowerRuntime.backward); autograd only carries d(features), d(words)."""
 
     @staticmethod
-    def forward(ctx, rt, inp, anchor, dense):
+    def forward(ctx, rt, inp, anchor, dense, pre=False):
         params = rt._params()
         feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)
         rt._outstanding += 1
-        ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense = rt, cfg, inp_used, ws, params, dense
+        ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense, ctx.pre = rt, cfg, inp_used, ws, params, dense, pre
+        outs = [feats]
         if dense:
-            return feats, words
-        return feats
+            outs.append(words)
+        if pre:
+            outs.append(rt.pre_features(cfg, ws).float())
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, dfeats, dwords=None):
+    def backward(ctx, dfeats, *rest):
         rt = ctx.rt
-        rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords)
+        rest = list(rest)
+        dwords = rest.pop(0) if ctx.dense else None
+        dpre = rest.pop(0) if ctx.pre else None
+        rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords, dpre)
         ctx.ws = None
         rt._outstanding = max(0, rt._outstanding - 1)
         if rt._outstanding == 0 and rt.grad_ready_hook is not None:
             rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
-        return None, None, None, None
+        return None, None, None, None, None
 
 
-def run_tower(rt, inp, dense=False):
+def run_tower(rt, inp, dense=False, pre=False):
     """Run the tower through autograd (training) or directly (no_grad / eval).  `anchor` is any trainable
     parameter: it makes the output require grad so backward is invoked.  dense=True also returns ln_final of every
-    token as bf16 [B*L, D]."""
+    token as bf16 [B*L, D]; pre=True also returns the pre-projection feature fp32 [B, width] (last)."""
     params = rt._params()
     if torch.is_grad_enabled():
         anchor = next((p for p in params.values() if p.requires_grad), None)
         if anchor is not None:
-            return _TowerFunction.apply(rt, inp, anchor, dense)
+            return _TowerFunction.apply(rt, inp, anchor, dense, pre)
     out = rt.forward(inp, params, dense)
-    return (out[0], out[4]) if dense else out[0]
+    outs = [out[0]]
+    if dense:
+        outs.append(out[4])
+    if pre:
+        outs.append(rt.pre_features(out[2], out[3]).float())
+    return outs[0] if len(outs) == 1 else tuple(outs)

@@ -271,6 +271,14 @@ int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sampl
                    void* dense_out, dc_stream_t stream);
 int dc_vit_backward(const dc_tower_cfg* cfg, const float* dfeatures, const void* ddense, const void* const* w_bf16,
                     const float* const* w_f32, float* const* grads, void* workspace, dc_stream_t stream);
+/* The pre-projection feature of the last forward held by `workspace`: ln_post(class token) for the ViT
+ * (`return_feature` of VisualTransformer.forward, visual_transformer.py:70,78-79), ln_final(EOT token) for the text
+ * tower; bf16 [batch, width].  dc_vit_backward_pre = dc_vit_backward with its gradient `dpre` (bf16 [batch, width],
+ * may be NULL) added to the gradient that reaches ln_post (used by SLIP's `predictor_sim`, slip.py:230-238). */
+int dc_tower_pre_features(const dc_tower_cfg* cfg, const void* workspace, void* out_bf16, dc_stream_t stream);
+int dc_vit_backward_pre(const dc_tower_cfg* cfg, const float* dfeatures, const void* dpre, const void* ddense,
+                        const void* const* w_bf16, const float* const* w_f32, float* const* grads, void* workspace,
+                        dc_stream_t stream);
 /* words_out (bf16 [batch*L, width], may be NULL): ln_final applied to EVERY token — the `words_feat` that
  * TextTransformer.forward returns with mask_type / return_dense (text_transformer.py:194-201).  When it was requested
  * in forward, backward must be called with dense=1 and dwords (bf16 [batch*L, width] or NULL = zero). */

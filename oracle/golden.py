@@ -16,6 +16,19 @@ DECLIP_CASES = {
 }
 
 
+SLIP_CASES = {
+    "slip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=9),
+}
+
+
+def slip_inputs(c):
+    from . import synth
+    sd = synth.slip_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"], t_layers=c["t_layers"])
+    images = torch.cat([synth.synth_images(c["batch"], seed=c["seed"], channels=6),
+                        synth.synth_images(c["batch"], seed=c["seed"] + 50, channels=3)], dim=1)
+    return sd, images, synth.synth_token_ids(c["batch"], seed=c["seed"])
+
+
 DEFILIP_CASES = {
     # DeCLIP batch + token-wise late interaction on all four (view, caption) combinations (return_filip, dense_aug)
     "defilip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=7, nn_size=1024),

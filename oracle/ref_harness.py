@@ -183,6 +183,38 @@ def reference_defilip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_b
             "bank": model.nn_replacer_text.bank.clone(), "bank_ptr": int(model.nn_replacer_text.bank_ptr)}, model
 
 
+def reference_slip_step(sd, images9, ids, embed_dim=512, v_layers=12, t_layers=12, sim_dim=256):
+    """Reference slip_vitb32 (return_sim) forward + the solver's loss (slip_solver.py:470-510: ClipInfoCELoss on the base
+    view + NT_Xent_gather on the two augmented views' sim features, weights 1 / 1) + backward.  CPU fp32, world 1."""
+    setup()
+    _ensure_pg()
+    os.environ.setdefault("SLURM_PROCID", "0")
+    os.environ.setdefault("SLURM_NTASKS", "1")
+    from prototype.loss_functions import NT_Xent_gather
+    from prototype.model import model_entry
+    cfg = dict(type="slip_vitb32", kwargs=dict(
+        image_encode=dict(embed_dim=embed_dim, layers=v_layers),
+        text_encode=dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=embed_dim, transformer_layers=t_layers),
+        clip=dict(use_allgather=True, return_sim=True, feature_dim=768, sim_dim=sim_dim)))
+    model = model_entry(cfg).train()
+    model.load_state_dict(sd, strict=True)
+
+    def _tok(texts, context_length=77, return_length=False, mask_type=None):
+        return ids
+    model.text_encoder.tokenize = _tok
+    B = images9.shape[0]
+    out = model({"images": images9, "captions": [["x"]] * B}, return_dict=True)
+    clip_loss, _ = clip_loss_fn()(*out["logits"])
+    s1, g1, s2, g2 = out["sim_features"]
+    simclr = NT_Xent_gather(B)(s1, g1, s2, g2)
+    loss = clip_loss + simclr
+    loss.backward()
+    return {"loss": loss.detach(), "parts": {"clip": clip_loss.detach(), "simclr": simclr.detach()}, "out": out,
+            "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None},
+            "stats": {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k}}, model
+
+
 def reference_filip_step(sd, images6, mlm_ids, mlm_labels, embed_dim=768, v_layers=12, t_layers=12, weights=None):
     """Reference filip_vitb32 (return_dense, select_topk, MLM tokenisation) forward + the solver's loss + backward."""
     setup()

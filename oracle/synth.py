@@ -147,6 +147,30 @@ def synth_mlm(ids, seed=0):
     return ids, labels
 
 
+def slip_state_dict(seed=0, embed_dim=512, v_layers=12, t_layers=12, feature_dim=768, sim_dim=256, hidden=4096):
+    """state_dict of the reference SLIP (slip.py:111-120,196-204): the CLIP keys with the text tower under `text_encoder.`
+    plus `predictor_sim` (Linear-BN x2, Linear, and the unused bn3)."""
+    sd = {}
+    for k, v in clip_vit_state_dict(seed=seed, embed_dim=embed_dim, v_layers=v_layers, t_layers=t_layers).items():
+        sd[("text_encoder." + k[len("encode_text."):]) if k.startswith("encode_text.") else k] = v
+
+    def lin(name, out_f, in_f):
+        sd[name + ".weight"] = _randn(name + ".weight", seed, (out_f, in_f), in_f ** -0.5)
+        sd[name + ".bias"] = _randn(name + ".bias", seed, (out_f,), 0.02)
+
+    def bn(name, c):
+        sd[name + ".weight"] = 1.0 + _randn(name + ".weight", seed, (c,), 0.1)
+        sd[name + ".bias"] = _randn(name + ".bias", seed, (c,), 0.02)
+        sd[name + ".running_mean"] = torch.zeros(c)
+        sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    lin("predictor_sim.linear1", hidden, feature_dim); bn("predictor_sim.bn1", hidden)
+    lin("predictor_sim.linear2", hidden, hidden); bn("predictor_sim.bn2", hidden)
+    lin("predictor_sim.linear3", sim_dim, hidden); bn("predictor_sim.bn3", hidden)
+    return sd
+
+
 def filip_extra_state_dict(seed=0, v_width=768, t_width=512, dense_dim=256, vocab=VOCAB):
     """Extra FILIP keys (filip.py:40-55): token mappings, dense logit scale, (unused) MLM head."""
     sd = {"logit_scale_dense": torch.tensor(math.log(1 / 0.07), dtype=torch.float32)}

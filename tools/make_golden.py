@@ -18,7 +18,7 @@ def main():
     torch.set_num_threads(os.cpu_count() or 8)
     os.makedirs(golden.GOLDEN_DIR, exist_ok=True)
     names = sys.argv[1:] or (list(golden.CASES) + list(golden.DECLIP_CASES) + list(golden.FILIP_CASES) +
-                             list(golden.RES_CASES) + list(golden.DEFILIP_CASES))
+                             list(golden.RES_CASES) + list(golden.DEFILIP_CASES) + list(golden.SLIP_CASES))
     if "nt_xent" in names or not sys.argv[1:]:
         from oracle import loss_ref
         ref_harness.setup()
@@ -50,6 +50,22 @@ def main():
         torch.save(blob, golden.path(name))
         print("%s: loss %.6f, %d grads, %.1fs -> %.1f KB" % (name, blob["loss"], len(blob["grads"]), time.time() - t0,
               os.path.getsize(golden.path(name)) / 1024))
+    for name in [n for n in names if n in golden.SLIP_CASES]:
+        c = golden.SLIP_CASES[name]
+        t0 = time.time()
+        sd, images, ids = golden.slip_inputs(c)
+        res, model = ref_harness.reference_slip_step(sd, images, ids, c["embed_dim"], c["v_layers"], c["t_layers"])
+        o = res["out"]
+        blob = {"case": c, "torch": torch.__version__,
+                "generator": "tools/make_golden.py via oracle/ref_harness.reference_slip_step (reference SLIP, CPU fp32)",
+                "loss": res["loss"].item(), "parts": {k: v.item() for k, v in res["parts"].items()},
+                "logits": [t.detach().clone() for t in o["logits"]],
+                "sim_features": [t.detach().clone() for t in o["sim_features"]],
+                "features": [t.detach().clone() for t in o["features"]],
+                "grads": golden.summarise_grads(res["grads"]), "stats": res["stats"]}
+        torch.save(blob, golden.path(name))
+        print("%s: loss %.6f parts %s, %d grads, %.1fs -> %.1f KB" % (name, blob["loss"], {k: round(v, 4) for k, v in
+              blob["parts"].items()}, len(blob["grads"]), time.time() - t0, os.path.getsize(golden.path(name)) / 1024))
     for name in [n for n in names if n in golden.DEFILIP_CASES]:
         c = golden.DEFILIP_CASES[name]
         t0 = time.time()
