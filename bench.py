@@ -79,7 +79,9 @@ def pick_cpu_threads():
 
 
 def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
-    """Times the oracle port of the reference step (fwd + ClipInfoCELoss + bwd, fp32) on the host cores."""
+    """Times the oracle port of the reference step (fwd + ClipInfoCELoss + bwd, fp32) on the host cores.  The optimiser
+    step is left out on purpose: at the sample batch of 32 a full AdamW over 151 M parameters (several seconds on a
+    host CPU) would be amortised over 16x fewer pairs than in the native arm's b = 512 step and inflate the ratio."""
     import torch
     from oracle import clip_ref, synth
     cores = pick_cpu_threads()
