@@ -64,6 +64,7 @@ SIGNATURES = {
     "dc_launch_count": (c_ll, []),
     "dc_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "dc_set_gemm_2cta": (c_int, [c_int]),
+    "dc_gemm_choose_splits": (c_int, [c_int, c_int, c_int]),
     "dc_set_attention_tc": (None, [c_int]),
     "dc_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                  c_void_p]),

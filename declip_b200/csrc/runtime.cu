@@ -96,6 +96,8 @@ extern "C" {
 
 int dc_version(void) { return 100; }
 
+int dc_gemm_choose_splits(int tiles, int total_kb, int workers) { return dc::choose_splits(tiles, total_kb, workers); }
+
 const char* dc_last_error(void) { return dc::g_err; }
 
 long long dc_launch_count(void) { return dc::g_launches.load(); }

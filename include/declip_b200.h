@@ -75,6 +75,9 @@ int dc_gemm_bf16(const dc_gemm_args* args, dc_stream_t stream);
  * previous setting.  Default 1 (measured +5-10 % over the 1-CTA 128x256 kernel, which remains the path for small
  * problems and can be forced with 0 or the DC_GEMM_2CTA=0 environment variable). */
 int dc_set_gemm_2cta(int enable);
+/* Host-side heuristic used for splits = 0: the split-K factor of an fp32-atomic GEMM with `tiles` output tiles and
+ * `total_kb` 64-deep k-blocks on `workers` persistent CTAs (clusters): minimises waves x (k-blocks per split + 3). */
+int dc_gemm_choose_splits(int tiles, int total_kb, int workers);
 /* 1 (default; env DC_ATTN_TC=0 disables) = tcgen05/TMEM attention core for L <= 128, 0 = the mma.sync core (L <= 80). */
 void dc_set_attention_tc(int enable);
 

@@ -51,3 +51,32 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_split_k_heuristic_is_wave_aware():
+    """Host logic of the weight-gradient GEMMs (csrc/internal.h choose_splits): never more waves x k-blocks than the
+    old fill-the-machine-twice rule, and the layer shapes of the bench land on the expected factors."""
+    from declip_b200 import _lib
+    lib = _lib.load()
+
+    def cost(tiles, kb, workers, s):
+        kbps = -(-kb // s)
+        eff = -(-kb // kbps)
+        return -(-tiles * eff // workers) * (kbps + 3)
+
+    def old(tiles, kb, workers):
+        if tiles >= workers:
+            return 1
+        return max(1, min(-(-2 * workers // tiles), (kb + 3) // 4))
+    cases = {"vit qkv": (27, 400, 8), "vit out": (9, 400, 8), "vit fc": (36, 400, 2), "txt qkv": (12, 616, 6),
+             "txt fc": (16, 616, 9), "patch embed": (9, 392, 8)}
+    for name, (tiles, kb, want) in cases.items():
+        s = lib.dc_gemm_choose_splits(tiles, kb, 74)
+        assert s == want, (name, s)
+        assert cost(tiles, kb, 74, s) <= cost(tiles, kb, 74, old(tiles, kb, 74)), name
+    assert lib.dc_gemm_choose_splits(300, 12, 74) == 1            # enough tiles: no split
+    assert lib.dc_gemm_choose_splits(1, 3, 74) == 1               # fewer than 4 k-blocks per split are never made
+    for tiles in range(1, 74):
+        for kb in (8, 64, 400, 616, 1000):
+            s = lib.dc_gemm_choose_splits(tiles, kb, 74)
+            assert 1 <= s <= max(1, (kb + 3) // 4) and cost(tiles, kb, 74, s) <= cost(tiles, kb, 74, 1)
