@@ -69,13 +69,3 @@ def test_defilip_step_matches_reference_golden(cuda_dev):
     assert all(w[0] > (0.95 if ("projector" in w[2] or "predictor" in w[2]) else 0.97) for w in worst), txt
     assert all(0.85 < w[1] < 1.15 for w in worst), txt
     assert model.nn_replacer_text.bank_ptr == g["bank_ptr"]
-
-
-def test_defilip_guards():
-    from declip_b200.model import model_entry
-    kw = dict(image_encode=dict(embed_dim=512, layers=1),
-              text_encode=dict(bpe_path=None, text_encode_type='Transformer', embed_dim=512, transformer_layers=1))
-    with pytest.raises(NotImplementedError):          # the reference reads an undefined word_features without MLM
-        model_entry(dict(type='defilip_vitb32', kwargs=dict(kw, clip=dict(use_allgather=True, return_filip=True, feature_dim=512))))
-    with pytest.raises(NotImplementedError):
-        model_entry(dict(type='slip_vitb32', kwargs=dict(kw, clip=dict(use_allgather=True))))

@@ -72,3 +72,19 @@ def test_logit_scale_clip_types():
     p.data.sub_(0.1)
     c.after()
     assert p.item() == pytest.approx(4.15)
+
+
+def test_factory_guards():
+    """Factories that cannot work raise at construction: DeFILIP's dense path without MLM reads an undefined
+    `word_features` in the reference (defilip.py:296-302,335); slip_res50 calls ModifiedResNet.forward with a
+    `return_feature` argument it does not have (modified_resnet.py:192)."""
+    kw = dict(image_encode=dict(embed_dim=512, layers=1),
+              text_encode=dict(bpe_path=None, text_encode_type='Transformer', embed_dim=512, transformer_layers=1))
+    with pytest.raises(NotImplementedError):
+        model_entry(dict(type='defilip_vitb32', kwargs=dict(kw, clip=dict(use_allgather=True, return_filip=True, feature_dim=512))))
+    with pytest.raises(NotImplementedError):
+        model_entry(dict(type='slip_res50', kwargs=dict(kw, clip=dict(use_allgather=True))))
+    with pytest.raises(KeyError):
+        model_entry(dict(type='no_such_model', kwargs={}))
+    m = model_entry(dict(type='slip_vitb32', kwargs=dict(kw, clip=dict(use_allgather=True, return_sim=True, feature_dim=768))))
+    assert any(k.startswith('text_encoder.') for k in m.state_dict()) and not any(k.startswith('encode_text.') for k in m.state_dict())
