@@ -16,7 +16,10 @@ typedef __nv_bfloat16 bf16;
 
 #ifndef DC_SPIN_LIMIT
 // A deadlocked mbarrier wait traps instead of hanging the GPU (≈ seconds of spinning).
-#define DC_SPIN_LIMIT (1u << 27)
+// mbar_wait traps instead of hanging the GPU: every try_wait parks the thread for up to DC_WAIT_HINT_NS, so the limit
+// corresponds to ~4 s (waits that return at once) .. ~84 s (every wait times out) — far beyond any legitimate wait.
+#define DC_SPIN_LIMIT (1u << 22)
+#define DC_WAIT_HINT_NS 20000
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -68,7 +71,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(DC_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
