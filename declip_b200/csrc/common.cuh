@@ -15,7 +15,6 @@ namespace dc {
 typedef __nv_bfloat16 bf16;
 
 #ifndef DC_SPIN_LIMIT
-// A deadlocked mbarrier wait traps instead of hanging the GPU (≈ seconds of spinning).
 // mbar_wait traps instead of hanging the GPU: every try_wait parks the thread for up to DC_WAIT_HINT_NS, so the limit
 // corresponds to ~4 s (waits that return at once) .. ~84 s (every wait times out) — far beyond any legitimate wait.
 #define DC_SPIN_LIMIT (1u << 22)
