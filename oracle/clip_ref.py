@@ -58,8 +58,8 @@ def _n_layers(sd, prefix):
     return n
 
 
-def encode_image(images, sd, prefix="visual.", heads=None, return_dense=False):
-    """VisualTransformer.forward — visual_transformer.py:55-82."""
+def encode_image(images, sd, prefix="visual.", heads=None, return_dense=False, return_feature=False):
+    """VisualTransformer.forward — visual_transformer.py:55-82 (ret = [x] + [dense_feat] + [feature], :74-82)."""
     w = sd[prefix + "conv1.weight"]
     width, patch = w.shape[0], w.shape[-1]
     heads = heads or width // 64
@@ -73,8 +73,10 @@ def encode_image(images, sd, prefix="visual.", heads=None, return_dense=False):
         x = resblock(x, sd, prefix + "transformer.resblocks.%d." % i, heads, None)
     dense = x[:, 1:, :]                                                # :68
     x = layer_norm(x[:, 0, :], sd[prefix + "ln_post.weight"], sd[prefix + "ln_post.bias"])   # :69
+    feature = x                                                        # :70
     x = x @ sd[prefix + "proj"]                                        # :72-73
-    return (x, dense) if return_dense else x
+    ret = [x] + ([dense] if return_dense else []) + ([feature] if return_feature else [])
+    return ret[0] if len(ret) == 1 else tuple(ret)
 
 
 def causal_mask(ctx):

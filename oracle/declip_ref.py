@@ -147,3 +147,29 @@ def defilip_loss(out, weights=LOSS_WEIGHTS, filip_weight=DEFILIP_FILIP_WEIGHT, w
     f = f / world
     parts = dict(parts, filip=f)
     return loss + f * filip_weight, parts
+
+
+def defilip_step(sd, images6, mlm_ids, mlm_labels, ids_aug, bank_dim_by_size):
+    """DEFILIP.forward (defilip.py:269-431: the DeCLIP forward with dense image / word tokens, `return_filip`, `dense_aug`)
+    + the solver's loss (defilip_loss) + backward, world size 1."""
+    from . import filip_ref
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k != "visual.conv1.weight" and
+                                                   "running_" not in k) for k, v in sd.items()}
+    stats = {k: v.detach().clone() for k, v in sd.items() if "running_" in k}
+    bank = Bank(bank_dim_by_size)
+    out = declip_forward(params, stats, images6, mlm_ids, mlm_labels, ids_aug, bank)
+    # token-wise late interaction on the four (view, caption) combinations               defilip.py:311-313,331-342
+    im1, im2 = torch.split(images6, [3, 3], dim=1)
+    _, d1 = clip_ref.encode_image(im1, params, return_dense=True)
+    _, d2 = clip_ref.encode_image(im2, params, return_dense=True)
+    _, w1 = clip_ref.encode_text(mlm_ids, params, return_dense=True)
+    _, w2 = clip_ref.encode_text(ids_aug, params, return_dense=True)
+    img = lambda t: F.linear(t, params["image_mapping.weight"], params["image_mapping.bias"])
+    txt = lambda t: F.linear(t, params["text_mapping.weight"], params["text_mapping.bias"])
+    dense = lambda a, b: filip_ref.weighted_dense_logits(a, b, params["logit_scale_dense"])[:2]
+    out["filip"] = dense(img(d1), txt(w1))
+    out["filip_aug"] = (*dense(img(d2), txt(w1)), *dense(img(d1), txt(w2)), *dense(img(d2), txt(w2)))
+    loss, parts = defilip_loss(out)
+    loss.backward()
+    return {"loss": loss.detach(), "parts": {k: v.detach() for k, v in parts.items()}, "out": out,
+            "grads": {k: p.grad for k, p in params.items() if p.grad is not None}, "bank_ptr": bank.ptr}

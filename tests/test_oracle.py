@@ -87,6 +87,47 @@ def test_declip_restatement_matches_reference_golden():
     assert abs(res["bank"].double().sum().item() - g["bank_checksum"]) < 1e-3   # FIFO enqueue of both text views
 
 
+def _check_grads(res, g, tol=3e-3):
+    assert set(res["grads"]) == set(g["grads"])
+    for k, ref in g["grads"].items():
+        mine = res["grads"][k].reshape(-1)
+        samp = mine[golden.sample_index(mine.numel())]
+        assert (samp - ref["sample"]).norm().item() <= tol * (ref["sample"].norm().item() + 1e-9) + 1e-7, k
+
+
+def test_slip_restatement_matches_reference_golden():
+    """oracle/slip_ref.py (SLIP.forward with the pre-projection feature + predictor_sim, ClipInfoCE + NT_Xent_gather)."""
+    from oracle import slip_ref
+    g = golden.load("slip_vitb32_l2_b8")
+    sd, images, ids = golden.slip_inputs(g["case"])
+    res = slip_ref.slip_step(sd, images, ids)
+    assert abs(res["loss"].item() - g["loss"]) <= 5e-5
+    for k, v in g["parts"].items():
+        assert abs(res["parts"][k].item() - v) <= 1e-4, k
+    for key in ("logits", "sim_features", "features"):
+        for a, b in zip(res["out"][key], g[key]):
+            torch.testing.assert_close(a.detach(), b, rtol=3e-4, atol=1e-3)
+    _check_grads(res, g)
+    for k, v in g["stats"].items():
+        torch.testing.assert_close(res["stats"][k], v, rtol=1e-4, atol=1e-5)
+
+
+def test_defilip_restatement_matches_reference_golden():
+    """oracle/declip_ref.defilip_step (DeCLIP forward + token-wise logits on four view x caption combinations)."""
+    from oracle import declip_ref
+    g = golden.load("defilip_vitb32_l2_b8")
+    sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.defilip_inputs(g["case"])
+    res = declip_ref.defilip_step(sd, images, mlm_ids, mlm_labels, ids_aug, bank)
+    assert abs(res["loss"].item() - g["loss"]) <= 5e-5
+    for k, v in g["parts"].items():
+        assert abs(res["parts"][k].item() - v) <= 1e-4, k
+    for key in ("logits", "logits_aug", "nn_text_logits", "filip", "filip_aug"):
+        for a, b in zip(res["out"][key], g[key]):
+            torch.testing.assert_close(a.detach(), b, rtol=3e-4, atol=1e-3)
+    _check_grads(res, g)
+    assert res["bank_ptr"] == g["bank_ptr"]
+
+
 def test_filip_restatement_matches_reference_golden():
     from oracle import filip_ref
     g = golden.load("filip_vitb32_l2_b8")
