@@ -48,7 +48,7 @@ class TowerCfg(ctypes.Structure):
 
 class AdamWEntry(ctypes.Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
-                ("numel", c_ull), ("lr", c_float), ("weight_decay", c_float)]
+                ("shadow", c_void_p), ("numel", c_ull), ("group", c_int), ("reserved", c_int)]
 
 
 class CastEntry(ctypes.Structure):
@@ -73,7 +73,8 @@ SIGNATURES = {
     "dc_colsum_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "dc_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "dc_multi_cast_f32_bf16": (c_int, [c_void_p, c_int, c_ull, c_void_p]),
-    "dc_adamw_multi": (c_int, [c_void_p, c_int, c_ull, c_float, c_float, c_float, c_int, c_void_p]),
+    "dc_adamw_multi": (c_int, [c_void_p, c_int, c_ull, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int,
+                              c_void_p]),
     "dc_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dc_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_void_p]),

@@ -772,15 +772,18 @@ int dc_dot_f32(const float* a, const float* b, size_t n, float* out, dc_stream_t
 // reference configs (experiments/*/config.yaml: optimizer type AdamW; prototype/optimizer/__init__.py:18-26).
 // One launch for every parameter tensor: blockIdx.y selects the tensor from a device table.
 namespace dc {
-__global__ void __launch_bounds__(256) adamw_multi_kernel(const dc_adamw_entry* __restrict__ table, float beta1,
-                                                          float beta2, float eps, float bc1, float bc2) {
+struct AdamWGroups { float lr[32]; float wd[32]; };
+
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const dc_adamw_entry* __restrict__ table, const AdamWGroups hp,
+                                                          float beta1, float beta2, float eps, float bc1, float bc2) {
   const dc_adamw_entry e = table[blockIdx.y];
   float* __restrict__ p = e.param;
   const float* __restrict__ g = e.grad;
   float* __restrict__ m = e.exp_avg;
   float* __restrict__ v = e.exp_avg_sq;
+  bf16* __restrict__ sh = static_cast<bf16*>(e.shadow);
   const size_t n = e.numel;
-  const float lr = e.lr, wd = e.weight_decay;
+  const float lr = hp.lr[e.group], wd = hp.wd[e.group];
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -802,6 +805,12 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const dc_adamw_entry* 
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (sh != nullptr) {   // shadows are 256-byte aligned slices of the tower's flat bf16 buffer
+      uint2 w;
+      w.x = pack_bf16x2(pv.x, pv.y);
+      w.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(sh)[i] = w;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const size_t i = (nv << 2) + threadIdx.x;
@@ -810,21 +819,30 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const dc_adamw_entry* 
     const float vk = beta2 * v[i] + (1.0f - beta2) * g[i] * g[i];
     pk -= step_size * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
     p[i] = pk; m[i] = mk; v[i] = vk;
+    if (sh != nullptr) sh[i] = __float2bfloat16(pk);
   }
 }
 }  // namespace dc
 
-extern "C" int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, float beta1,
-                              float beta2, float eps, int step, dc_stream_t stream) {
+extern "C" int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel,
+                              const float* lr_host, const float* wd_host, int n_groups, float beta1, float beta2,
+                              float eps, int step, dc_stream_t stream) {
   if (n_tensors <= 0) return 0;
   if (step < 1) return dc::set_error("adamw: step must be >= 1");
+  if (n_groups < 1 || n_groups > 32 || lr_host == nullptr || wd_host == nullptr)
+    return dc::set_error("adamw: 1..32 param groups with host lr / weight_decay arrays");
+  dc::AdamWGroups hp;
+  for (int i = 0; i < 32; ++i) {
+    hp.lr[i] = i < n_groups ? lr_host[i] : 0.f;
+    hp.wd[i] = i < n_groups ? wd_host[i] : 0.f;
+  }
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   int bx = static_cast<int>((max_numel / 4 + 255) / 256);
   if (bx > 128) bx = 128;
   if (bx < 1) bx = 1;
   dim3 grid(bx, n_tensors);
-  dc::adamw_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, beta1, beta2, eps, bc1, bc2);
+  dc::adamw_multi_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, hp, beta1, beta2, eps, bc1, bc2);
   DC_CHECK_LAUNCH("adamw_multi");
   return 0;
 }

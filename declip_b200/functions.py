@@ -11,6 +11,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, ops
+from .runtime import weight_shadow
 
 _PTR = ctypes.c_void_p
 
@@ -442,9 +443,10 @@ class MaskedLMHead(torch.autograd.Function):
         n = rows.numel()
         v, d = weight.shape
         vp = (v + 7) // 8 * 8
-        w16 = torch.zeros(vp, d, device=words.device, dtype=torch.bfloat16)
-        _lib.check(lib.dc_cast_f32_bf16(_PTR(weight.data_ptr()), _PTR(w16.data_ptr()), weight.numel(), _stream()),
-                   "dc_cast_f32_bf16")
+        if n == 0:
+            raise RuntimeError("declip_b200: MLM head called with no masked token in the batch (declip.py:326-334 "
+                               "would return nan)")
+        w16 = weight_shadow(weight, pad_rows=vp)       # [vp, d] bf16, re-cast only when the master changed
         bpad = torch.zeros(vp, device=words.device, dtype=torch.float32)
         bpad[:v] = bias
         x = torch.empty(n, d, device=words.device, dtype=torch.bfloat16)
@@ -518,7 +520,7 @@ class LinearBF16In(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        w16 = cast_bf16(weight.contiguous())
+        w16 = weight_shadow(weight)
         x = x.contiguous()
         y = ops.gemm(x, w16, bias=bias, epilogue=ops.EPI_F32)
         ctx.save_for_backward(x, w16)

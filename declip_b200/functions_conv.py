@@ -6,6 +6,7 @@ import torch
 
 from . import _lib, ops
 from .functions import cast_bf16
+from .runtime import weight_shadow
 
 _PTR = ctypes.c_void_p
 
@@ -52,7 +53,7 @@ class Conv1x1(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight):
-        w16 = cast_bf16(weight.reshape(weight.shape[0], -1).contiguous())
+        w16 = weight_shadow(weight).view(weight.shape[0], -1)      # [cout, cin] bf16, re-cast only when the master changed
         y = ops.gemm(x, w16)
         ctx.save_for_backward(x, w16)
         ctx.wshape = tuple(weight.shape)
@@ -190,7 +191,7 @@ class LinearBF16(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        w16 = cast_bf16(weight.contiguous())
+        w16 = weight_shadow(weight)
         x = x.contiguous()
         y = ops.gemm(x, w16, bias=bias)
         ctx.save_for_backward(x, w16)

@@ -41,6 +41,40 @@ TEXT_GRADS = ("token_embedding.weight", "positional_embedding", "ln_final.weight
               "text_projection.weight", "text_projection.bias")
 
 
+def register_shadow(p, shadow):
+    """Attach a bf16 mirror (a tensor whose first p.numel() elements follow p's layout) to a parameter.  Whoever
+    updates the fp32 master either bumps p._version (torch.optim, copy_, load_state_dict) — the owner then re-casts
+    — or rewrites the mirror itself and records the version it corresponds to (FusedAdamW)."""
+    p._dc_shadow = shadow
+    p._dc_shadow_version = -1
+
+
+def shadow_current(p, ptr=None):
+    sh = getattr(p, "_dc_shadow", None)
+    return sh is not None and (ptr is None or sh.data_ptr() == ptr) and p._dc_shadow_version == p._version
+
+
+def weight_shadow(p, pad_rows=0):
+    """bf16 mirror of a head / conv weight outside the two towers, cast only when the master changed (the towers
+    keep theirs in one flat buffer, TowerRuntime._prepare).  pad_rows > 0: the mirror has that many leading rows
+    (zero tail) for GEMM operands that need a 16-byte-aligned or padded extent."""
+    sh = getattr(p, "_dc_shadow", None)
+    rows = max(pad_rows, p.shape[0]) if p.dim() > 1 else p.shape[0]
+    shape = (rows,) + tuple(p.shape[1:])
+    if sh is None or sh.device != p.device or tuple(sh.shape) != shape:
+        sh = torch.zeros(shape, device=p.device, dtype=torch.bfloat16)
+        register_shadow(p, sh)
+    if p._dc_shadow_version != p._version:
+        lib = _lib.init(p.device.index if p.device.index is not None else torch.cuda.current_device())
+        src = p.detach()
+        if not src.is_contiguous() or src.dtype != torch.float32:
+            src = src.float().contiguous()
+        _lib.check(lib.dc_cast_f32_bf16(_PTR(src.data_ptr()), _PTR(sh.data_ptr()), src.numel(), _stream()),
+                   "dc_cast_f32_bf16")
+        p._dc_shadow_version = p._version
+    return sh
+
+
 class TowerRuntime:
     """Per-module state for dc_{vit,text}_{forward,backward}.  `kind` is 'vit' or 'text'."""
 
@@ -93,6 +127,9 @@ class TowerRuntime:
         self.cast_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self.cast_n, self.cast_max = len(self.bf16_names), max_numel
         self.w_bf16 = _ptr_array([self.shadow.data_ptr() + 2 * o for o in offs])
+        self._shadow_ptrs = [self.shadow.data_ptr() + 2 * o for o in offs]
+        for n, o in zip(self.bf16_names, offs):     # FusedAdamW rewrites these slices in its own pass (optim.py)
+            register_shadow(params[n], self.shadow[o:o + params[n].numel()])
         self.w_f32 = _ptr_array([params[n].data_ptr() for n in self.f32_names])
         # flat fp32 gradient buffer in the executor's table order
         goffs, gtotal = [], 0
@@ -107,12 +144,16 @@ class TowerRuntime:
 
     def refresh_shadows(self, params):
         """fp32 master -> bf16 shadow for every GEMM weight (one launch); skipped when nothing changed."""
-        versions = tuple(params[n]._version for n in self.bf16_names)
-        if versions == self._versions:
+        ps = [params[n] for n in self.bf16_names]
+        if all(shadow_current(p, ptr) for p, ptr in zip(ps, self._shadow_ptrs)):
             return
         _lib.check(self.lib.dc_multi_cast_f32_bf16(_PTR(self.cast_table.data_ptr()), self.cast_n, self.cast_max, _stream()),
                    "dc_multi_cast_f32_bf16")
-        self._versions = versions
+        for p, ptr, n in zip(ps, self._shadow_ptrs, self.bf16_names):
+            if getattr(p, "_dc_shadow", None) is None or p._dc_shadow.data_ptr() != ptr:
+                off = (ptr - self.shadow.data_ptr()) // 2
+                register_shadow(p, self.shadow[off:off + p.numel()])
+            p._dc_shadow_version = p._version
 
     def cfg(self, batch):
         c = TowerCfg()

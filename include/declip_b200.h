@@ -104,14 +104,18 @@ int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsign
 
 /* Fused multi-tensor AdamW step (torch.optim.AdamW semantics: p *= 1 - lr*wd; Adam moments; bias correction from
  * `step`): the optimiser of the reference configs (config.yaml optimizer.type AdamW).  table (device): one entry per
- * parameter tensor, fp32 everywhere; lr / weight_decay per entry carry the reference's param groups
- * (utils/misc.py:267-412: no decay on biases / norms / logit_scale). */
+ * parameter tensor, fp32 master / moments; `group` indexes the host arrays lr[] / weight_decay[] (n_groups <= 32,
+ * passed to the kernel by value, so a per-iteration LR schedule never touches the device table) that carry the
+ * reference's param groups (utils/misc.py:267-412: no decay on biases / norms / logit_scale).  `shadow` (may be NULL)
+ * is the bf16 copy of the parameter that the tensor-core GEMMs read: the kernel rewrites it from the updated master
+ * in the same pass, so a step never leaves a stale shadow behind. */
 typedef struct {
-  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
-  unsigned long long numel; float lr; float weight_decay;
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; void* shadow;
+  unsigned long long numel; int group; int reserved;
 } dc_adamw_entry;
-int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, float beta1,
-                   float beta2, float eps, int step, dc_stream_t stream);
+int dc_adamw_multi(const dc_adamw_entry* table_dev, int n_tensors, unsigned long long max_numel, const float* lr_host,
+                   const float* wd_host, int n_groups, float beta1, float beta2, float eps, int step,
+                   dc_stream_t stream);
 
 /* ------------------------------------------------------------------ attention (L <= 128, head_dim 64)
  * tcgen05/TMEM core (attention_tc.cu) for L <= 128 and even head counts when L <= 64; mma.sync core (L <= 80) otherwise

@@ -10,9 +10,11 @@ CASES = {
     # name: dict(batch, v_layers, t_layers, embed_dim, seed)
     "clip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=1),
     "clip_vitb32_l12_b32": dict(batch=32, v_layers=12, t_layers=12, embed_dim=512, seed=0),   # BASELINE configs[0]
+    "clip_vitb32_l12_b512": dict(batch=512, v_layers=12, t_layers=12, embed_dim=512, seed=3),  # configs[1] per-GPU shape
 }
 DECLIP_CASES = {
     "declip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=512, seed=2, nn_size=1024),
+    "declip_vitb32_l12_b64": dict(batch=64, v_layers=12, t_layers=12, embed_dim=512, seed=12, nn_size=4096),  # configs[2] depth
 }
 
 
@@ -46,6 +48,7 @@ def defilip_inputs(c):
 
 FILIP_CASES = {
     "filip_vitb32_l2_b8": dict(batch=8, v_layers=2, t_layers=2, embed_dim=768, seed=4),
+    "filip_vitb32_l12_b64": dict(batch=64, v_layers=12, t_layers=12, embed_dim=768, seed=14),   # configs[4] depth
 }
 
 
@@ -61,6 +64,7 @@ def filip_inputs(c):
 
 RES_CASES = {
     "clip_res50_l1111_b4": dict(batch=4, layers=(1, 1, 1, 1), t_layers=2, embed_dim=1024, seed=6),
+    "clip_res50_l3463_b32": dict(batch=32, layers=(3, 4, 6, 3), t_layers=12, embed_dim=1024, seed=16),   # configs[3] depth
 }
 
 

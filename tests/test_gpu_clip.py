@@ -112,16 +112,66 @@ def test_grad_accumulation_and_zero_grad_modes(cuda_dev):
             assert torch.allclose(p.grad, g1[k], rtol=2e-2, atol=1e-6), k
 
 
-def test_optimizer_step_updates_shadows(cuda_dev):
-    """bf16 shadows are refreshed after an in-place optimizer update (version counter)."""
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw", "fused_adamw"])
+def test_optimizer_step_updates_shadows(cuda_dev, opt_name):
+    """After an optimizer step the bf16 GEMM shadows equal the cast of the updated fp32 masters — through the version
+    counter for torch.optim, through the kernel's own shadow write for FusedAdamW — and step-2 logits follow the
+    CPU oracle evaluated on the updated state_dict."""
+    from declip_b200.optim import FusedAdamW
+    from oracle import clip_ref
     case = dict(batch=4, v_layers=1, t_layers=1, embed_dim=512, seed=11)
     model, sd, images, ids = _build(case, cuda_dev)
-    opt = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.5)
-    _, _, loss0, _ = _step(model, images, ids)
-    opt.step()
-    opt.zero_grad()
-    _, _, loss1, _ = _step(model, images, ids)
+    ps = [p for p in model.parameters() if p.requires_grad]
+    opt = {"sgd": lambda: torch.optim.SGD(ps, lr=0.5), "adamw": lambda: torch.optim.AdamW(ps, lr=1e-2),
+           "fused_adamw": lambda: FusedAdamW(ps, lr=1e-2)}[opt_name]()
+    for _ in range(2):
+        _, _, loss0, _ = _step(model, images, ids)
+        before = {k: p.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        opt.zero_grad()
+    li, lt, loss1, _ = _step(model, images, ids)
     assert loss1.item() != loss0.item()
+    checked = 0
+    for tower in (model.visual, model.encode_text):
+        rt = tower._rt
+        params = rt._params()
+        for n, ptr in zip(rt.bf16_names, rt._shadow_ptrs):
+            p = params[n]
+            off = (ptr - rt.shadow.data_ptr()) // 2
+            assert torch.equal(rt.shadow[off:off + p.numel()], p.detach().bfloat16().reshape(-1)), n
+            if p.requires_grad:
+                assert not torch.equal(p.detach(), before[[k for k, q in model.named_parameters() if q is p][0]]), n
+            checked += 1
+    assert checked == 2 * 4 + 3
+    out = clip_ref.clip_step({k: v.detach().cpu() for k, v in model.state_dict().items()}, images.cpu(), ids.cpu())
+    assert abs(loss1.item() - out["loss"].item()) <= 5e-3
+    assert _cos(li.cpu(), out["logits_per_image"]) > 0.999
+
+
+def test_fused_adamw_training_matches_torch_adamw(cuda_dev):
+    """Three training steps: FusedAdamW vs torch.optim.AdamW on two copies of the model — same loss trajectory and
+    the same GEMM weights (this is what a stale bf16 shadow would break)."""
+    from declip_b200.optim import FusedAdamW
+    case = dict(batch=4, v_layers=1, t_layers=1, embed_dim=512, seed=13)
+    runs = []
+    for make in (lambda ps: torch.optim.AdamW(ps, lr=3e-3, weight_decay=0.1), lambda ps: FusedAdamW(ps, lr=3e-3, weight_decay=0.1)):
+        model, sd, images, ids = _build(case, cuda_dev)
+        opt = make([p for p in model.parameters() if p.requires_grad])
+        losses = []
+        for _ in range(3):
+            _, _, loss, _ = _step(model, images, ids)
+            losses.append(loss.item())
+            opt.step()
+            opt.zero_grad()
+        runs.append((losses, {k: p.detach().clone() for k, p in model.named_parameters()}))
+    (l_ref, w_ref), (l_mine, w_mine) = runs
+    assert abs(l_ref[0] - l_mine[0]) < 1e-6
+    assert l_ref[2] != l_ref[0]
+    for a, b in zip(l_ref, l_mine):
+        assert abs(a - b) < 2e-3, (l_ref, l_mine)
+    for k in w_ref:          # Adam normalises the update to ~lr per element: compare in units of lr
+        assert (w_ref[k] - w_mine[k]).abs().max().item() < 7 * 3e-3, k
+        assert _cos(w_ref[k] - sd[k].to(cuda_dev), w_mine[k] - sd[k].to(cuda_dev)) > 0.98 or not w_ref[k].requires_grad, k
 
 
 def test_full_size_properties(cuda_dev):

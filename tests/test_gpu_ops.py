@@ -263,3 +263,55 @@ def test_fused_adamw_matches_torch(cuda_dev):
         ref.step()
     for p, q in zip(ps, qs):
         assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (p - q).abs().max()
+
+
+def test_fused_adamw_state_dict_and_skipped_params(cuda_dev):
+    """torch.optim.AdamW checkpoints store `step` as a tensor; a parameter with grad=None on some iteration keeps its
+    own step count (torch semantics) instead of raising."""
+    from declip_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    ps = [torch.randn(s, device=cuda_dev).requires_grad_(True) for s in [(64, 32), (32,), (5,)]]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    ref = torch.optim.AdamW(qs, lr=1e-3, weight_decay=0.05)
+    for _ in range(2):
+        for q in qs:
+            q.grad = torch.randn_like(q)
+        ref.step()
+    with torch.no_grad():
+        for p, q in zip(ps, qs):
+            p.copy_(q)
+    mine = FusedAdamW(ps, lr=1e-3, weight_decay=0.05)
+    mine.load_state_dict(ref.state_dict())                 # tensor-valued `step`
+    for it in range(3):
+        for i, (p, q) in enumerate(zip(ps, qs)):
+            if it == 1 and i == 2:                         # the third parameter skips one iteration
+                p.grad = q.grad = None
+                continue
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        mine.step()
+        ref.step()
+    for p, q in zip(ps, qs):
+        assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (p - q).abs().max()
+    assert int(mine.state[ps[0]]["step"]) == 5 and int(mine.state[ps[2]]["step"]) == 4
+
+
+def test_fused_adamw_rewrites_registered_shadow(cuda_dev):
+    """The kernel refreshes a registered bf16 mirror (padded layouts included) and bumps the version counter."""
+    from declip_b200.optim import FusedAdamW
+    from declip_b200.runtime import shadow_current, weight_shadow
+    torch.manual_seed(2)
+    w = torch.nn.Parameter(torch.randn(49, 512, device=cuda_dev))
+    sh = weight_shadow(w, pad_rows=56)
+    assert sh.shape == (56, 512) and torch.equal(sh[:49], w.detach().bfloat16()) and not sh[49:].any()
+    opt = FusedAdamW([w], lr=1e-2)
+    v0 = w._version
+    w.grad = torch.randn_like(w)
+    opt.step()
+    assert w._version == v0 + 1 and shadow_current(w)
+    assert weight_shadow(w, pad_rows=56) is sh                       # no re-cast needed ...
+    assert torch.equal(sh[:49], w.detach().bfloat16()) and not sh[49:].any()    # ... because the kernel wrote it
+    with torch.no_grad():
+        w.mul_(2.0)                                                    # any other in-place update re-casts lazily
+    assert not shadow_current(w)
+    assert torch.equal(weight_shadow(w, pad_rows=56)[:49], w.detach().bfloat16())
