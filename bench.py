@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — image-text pairs/s of one CLIP ViT-B/32 training step (BASELINE.json metric).
+"""bench.py — image-text pairs/s of one training step of the CLIP-family dual encoder (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config clip|declip|filip|res50]
+                    [--batch B]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
 
-native arm   : the CUDA path of this repo through its public API — CLIP.forward (dict in, two logit
-               strips out) + ClipInfoCELoss + backward + flat-bucket gradient all-reduce + AdamW step —
-               on synthetic 224x224 images / 77-token ids, random-init ViT-B/32 + 12-layer text tower,
-               bf16 storage / fp32 accumulate, per-GPU batch 512 (BASELINE configs[1]: global 4096 on 8 GPUs).
+--config (default clip = BASELINE configs[1], the configuration the metric is quoted on):
+    clip   CLIP ViT-B/32 + 12L text transformer, ClipInfoCELoss                       (configs[1])
+    declip DeCLIP ViT-B/32: two image views, MLM, NN bank (65536), SimSiam, 12 strips   (configs[2])
+    res50  CLIP ModifiedResNet-50 image tower + 12L text transformer, E = 1024          (configs[3])
+    filip  FILIP ViT-B/32: global + token-wise late-interaction logits, E = 768         (configs[4])
+native arm   : the CUDA path of this repo through its public API — model(dict) -> logits/dict, the solver's loss
+               composition, backward, bucketed gradient all-reduce, FusedAdamW, logit-scale clamp — on synthetic
+               224x224 images / 77-token ids, random init, bf16 storage / fp32 accumulate, per-GPU batch 512.
                `value` = inputs resident in HBM; `e2e` = pinned-host inputs copied H2D every step
                (double-buffered on a copy stream) + D2H read of the loss, all inside the timed region.
-reference arm: the reference's own CPU implementation of the same step (oracle restatement of its modules,
-               oracle/clip_ref.py — the Python reference cannot travel to the GPU box), all host cores,
-               a bounded sample (bs 32) per step.
+reference arm: the reference's own modules (staged copy under oracle/_ref, see oracle/build_ref.py; the oracle
+               restatement when that is absent) running the same step on the host cores: fixed thread count (the
+               physical cores of one socket), a bounded sample batch per step, median step time.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -25,10 +30,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-TRAIN_GFLOP_PER_PAIR = 43.9   # fwd 14.78 + 2x bwd, frozen conv1 bwd skipped
-CPU_SAMPLE_BATCH = 32         # BASELINE configs[0]
-
 
 _T0 = time.time()
 
@@ -49,76 +50,153 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="clip", choices=["clip", "declip", "filip", "res50"])
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+# ------------------------------------------------------------------------------------------------ workload arithmetic
+VIT_FWD, TEXT_FWD, PATCH_FWD = 8.82, 5.96, 0.231          # GFLOP per sample, SURVEY.md §8(d)
+
+
+def resnet50_fwd_gflop(res=224, width=64, layers=(3, 4, 6, 3), embed=1024):
+    """2 x MACs of ModifiedResNet-50 + AttentionPool2d per image (modified_resnet.py:150-214, shape walk SURVEY App. C)."""
+    hw = (res // 2) ** 2
+    f = 2.0 * hw * (27 * width // 2 + 9 * (width // 2) * (width // 2) + 9 * (width // 2) * width)
+    hw //= 4
+    inpl = width
+    for planes, blocks, stride in zip((width, 2 * width, 4 * width, 8 * width), layers, (1, 2, 2, 2)):
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            hw_out = hw // (s * s)
+            f += 2.0 * (hw * inpl * planes + hw * 9 * planes * planes + hw_out * planes * 4 * planes)
+            if s > 1 or inpl != 4 * planes:
+                f += 2.0 * hw_out * inpl * 4 * planes
+            inpl, hw = 4 * planes, hw_out
+    c = width * 32
+    f += 2.0 * ((1 + 2 * (hw + 1)) * c * c + c * embed) + 4.0 * (hw + 1) * c      # q (1 token), k, v, c_proj, scores
+    return f / 1e9
+
+
+def train_gflop_per_pair(config, n_global):
+    """Algorithmic FLOPs of one training step per image-text pair (fwd + 2 x bwd; no wgrad/dgrad for the frozen conv1)."""
+    if config == "clip":
+        return 43.9
+    if config == "res50":
+        return 3.0 * (resnet50_fwd_gflop() + TEXT_FWD)
+    if config == "declip":
+        # two image views + two caption passes; MLM head on the ~15 % masked positions only (gathered rows — the
+        # reference runs it densely on all 77 tokens: 3.9 GFLOP more per pair); NN bank 3 lookups; SimSiam heads
+        fwd = 2 * VIT_FWD + 2 * TEXT_FWD + 0.05 + 0.20 + 0.015
+        return 3.0 * fwd - 2 * 2 * PATCH_FWD
+    if config == "filip":
+        late = 2.0 * (49 + 77) * 256 * n_global * 16 / 1e9             # [B n, 256] x [N 16, 256]^T, both directions
+        return 43.9 + 3.0 * late + 3.0 * 2.0 * (49 * 768 + 77 * 512) * 256 / 1e9
+    raise ValueError(config)
+
+
+WORKLOAD_TEXT = {
+    "clip": "CLIP ViT-B/32 + 12L text transformer training step: fwd + ClipInfoCELoss + bwd + grad all-reduce + AdamW "
+            "(BASELINE configs[1])",
+    "declip": "DeCLIP ViT-B/32 training step: 2 image views + MLM caption + EDA-view caption, SimSiam heads, NN bank "
+              "65536, 12 logit strips, DeclipCriterion (0.4/0.2/0.2/0.2) + bwd + all-reduce + AdamW (BASELINE configs[2])",
+    "res50": "CLIP ModifiedResNet-50 + 12L text transformer (E=1024) training step: fwd + ClipInfoCELoss + bwd + "
+             "all-reduce + AdamW (BASELINE configs[3])",
+    "filip": "FILIP ViT-B/32 (E=768) training step: global + token-wise late-interaction logits (top-16), FilipCriterion "
+             "(clip 1.0 / dense 1.0) + bwd + all-reduce + AdamW (BASELINE configs[4])",
+}
+CPU_SAMPLE_BATCH = {"clip": 32, "declip": 16, "filip": 32, "res50": 16}
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
-def pick_cpu_threads():
-    """The reference's CPU path is PyTorch eager; more threads is not monotonically faster on these GEMM sizes
-    (128 threads measured 40x SLOWER than 8 on the GPU box).  Time the path's dominant op (the c_fc Linear of a
-    bs-32 ViT step, [1600x768]x[768x3072]) at a few thread counts and use the fastest — the best the host can do."""
-    import torch
-    total = os.cpu_count() or 1
-    cands = sorted({c for c in (4, 8, 16, 32, 64, total) if c <= total})
-    a, w = torch.randn(1600, 768), torch.randn(3072, 768)
-    best, best_t = cands[0], float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        torch.nn.functional.linear(a, w)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            torch.nn.functional.linear(a, w)
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = c, dt
-    log("cpu arm: picked %d of %d host threads" % (best, total))
-    return best
+def one_socket_cores():
+    """Physical cores of socket 0 (falls back to half the logical CPUs): a fixed, reproducible thread count — PyTorch
+    eager on these GEMM sizes does not get faster across sockets / hyper-threads (round 1 saw 2.5x run-to-run swings
+    from a micro-benchmark-picked count)."""
+    cores = set()
+    try:
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id"):
+                core = int(line.split(":")[1])
+            elif not line.strip():
+                if phys == 0 and core is not None:
+                    cores.add(core)
+                phys = core = None
+    except Exception:
+        pass
+    n = len(cores) or max(1, (os.cpu_count() or 2) // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, n)
 
 
-def cpu_reference_steps(steps, warmup, batch=CPU_SAMPLE_BATCH):
-    """Times the oracle port of the reference step (fwd + ClipInfoCELoss + bwd, fp32) on the host cores.  The optimiser
-    step is left out on purpose: at the sample batch of 32 a full AdamW over 151 M parameters (several seconds on a
-    host CPU) would be amortised over 16x fewer pairs than in the native arm's b = 512 step and inflate the ratio."""
+def cpu_reference_steps(config, steps, warmup):
+    """Times the reference's own step (fwd + the solver's loss + bwd, fp32) on the host cores.  The optimiser step is
+    left out on purpose: at the bounded sample batch a full AdamW over 151 M parameters would be amortised over 16-32x
+    fewer pairs than in the native arm's b = 512 step and inflate the GPU/CPU ratio."""
     import torch
-    from oracle import clip_ref, synth
-    cores = pick_cpu_threads()
+    cores = one_socket_cores()
     torch.set_num_threads(cores)
-    sd = synth.clip_vit_state_dict(seed=0)
-    images = synth.synth_images(batch, seed=0)
-    ids = synth.synth_token_ids(batch, seed=0)
-    log("cpu arm: %d threads, warm-up" % cores)
-    for _ in range(warmup):
-        tw = time.perf_counter()
-        clip_ref.clip_step(sd, images, ids)
-        tw = time.perf_counter() - tw
-    steps = max(1, min(steps, int(25.0 / max(tw, 1e-3))))     # bound the sample to ~25 s of CPU work
+    batch = CPU_SAMPLE_BATCH[config]
+    kind, what = "reference", "reference modules (oracle/_ref)"
+    stepper = None
+    try:
+        from oracle import ref_harness
+        if not ref_harness.available():
+            raise RuntimeError("no staged reference")
+        stepper = ref_harness.Stepper(config, batch)
+        step = stepper.step
+        if "/root/reference" in ref_harness.REF_ROOT:
+            what = "reference modules (/root/reference)"
+    except Exception as ex:          # noqa: BLE001 - fall back to the restatement, and say so
+        log("cpu arm: reference modules unavailable (%r); timing the oracle restatement" % (ex,))
+        if config != "clip":
+            raise
+        from oracle import clip_ref, synth
+        kind, what = "port", "oracle/clip_ref.py restatement"
+        sd = synth.clip_vit_state_dict(seed=0)
+        images, ids = synth.synth_images(batch, seed=0), synth.synth_token_ids(batch, seed=0)
+        step = lambda: clip_ref.clip_step(sd, images, ids)
+    log("cpu arm: %s, %d threads, warm-up" % (what, cores))
+    tw = 0.0
+    for _ in range(max(1, warmup)):
+        t = time.perf_counter()
+        step()
+        tw = time.perf_counter() - t
+    steps = max(5, min(steps, 8))
+    steps = max(3, min(steps, int(40.0 / max(tw, 1e-3))))      # bound the sample to ~40 s of CPU work
     log("cpu arm: warm step %.2fs -> timing %d steps" % (tw, steps))
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
-        clip_ref.clip_step(sd, images, ids)
-    dt = time.perf_counter() - t0
-    return {"value": batch * steps / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of bs %d (fwd+loss+bwd, fp32, oracle/clip_ref.py) in %.1f s" % (steps, batch, dt),
-            "ms_per_step": 1e3 * dt / steps}
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": batch / med, "unit": "pairs/s", "cores": cores, "kind": kind,
+            "sample": "median of %d steps of bs %d (fwd + loss + bwd, fp32, %s); min %.2f s max %.2f s" %
+                      (steps, batch, what, times[0], times[-1]),
+            "ms_per_step": 1e3 * med, "steps": steps}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    cb = cpu_reference_steps(steps, warm)
-    steps = int(cb["sample"].split()[0])
+    cb = cpu_reference_steps(args.config, args.steps, max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": "image-text pairs/sec", "value": cb["value"], "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"],
+        "n_gpus": args.gpus, "steps": cb["steps"], "warmup": max(1, min(args.warmup, 2)), "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CLIP ViT-B/32 + 12L text transformer, one training step (fwd+ClipInfoCELoss+bwd)",
-                   "sample_batch": CPU_SAMPLE_BATCH, "seq_len": 77, "image": "3x224x224"},
+        "config": {"workload": WORKLOAD_TEXT[args.config].replace(" + grad all-reduce + AdamW", "").replace(" + all-reduce + AdamW", ""),
+                   "name": args.config, "sample_batch": CPU_SAMPLE_BATCH[args.config], "seq_len": 77, "image": "3x224x224"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -190,13 +268,106 @@ def synthetic_token_ids(batch, gen, ctx=77):
     return ids
 
 
+def build_workload(config, dev, b, world):
+    """(model, loss_fn(model_out) -> scalar loss, host-input factory, inputs -> model input dict)."""
+    import torch
+    from declip_b200.loss_functions import ClipInfoCELoss, DeclipCriterion, FilipCriterion
+    from declip_b200.model import model_entry
+    text = dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False))
+    if config == "clip":
+        cfg = dict(type='clip_vitb32', kwargs=dict(image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **text),
+                                                   clip=dict(use_allgather=True)))
+    elif config == "res50":
+        cfg = dict(type='clip_res50', kwargs=dict(image_encode=dict(embed_dim=1024, use_sync_bn=False, bn_group_size=1),
+                                                  text_encode=dict(embed_dim=1024, **text), clip=dict(use_allgather=True)))
+    elif config == "declip":
+        cfg = dict(type='declip_vitb32', kwargs=dict(
+            image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **text),
+            clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=512, nn_size=65536)))
+    else:
+        cfg = dict(type='filip_vitb32', kwargs=dict(
+            image_encode=dict(embed_dim=768), text_encode=dict(embed_dim=768, **text),
+            clip=dict(use_allgather=True, text_mask_type='MLM', return_dense=True, select_topk=True, feature_dim=768,
+                      mask_rate=0.5, patch_number=14)))
+    model = model_entry(cfg).to(dev).train()
+    channels = 6 if config in ("declip", "filip") else 3          # two stacked views (declip.py:199, filip.py:112)
+    two_captions = config == "declip"
+
+    def host_inputs(gen):
+        h = {"images": torch.randn(b, channels, 224, 224, generator=gen).pin_memory(),
+             "token_ids": synthetic_token_ids(b, gen).pin_memory()}
+        if two_captions:
+            h["token_ids_aug"] = synthetic_token_ids(b, gen).pin_memory()
+        return h
+
+    if config in ("clip", "res50"):
+        crit = ClipInfoCELoss()
+        run = lambda m, inp: crit(*m({"captions": None, **inp}))[0]
+    elif config == "declip":
+        crit = DeclipCriterion(world_size=1)                      # the step divides by world itself (clip_solver.py:418)
+        run = lambda m, inp: crit(m({"captions": None, **inp}, return_dict=True))[0]
+    else:
+        crit = FilipCriterion(weights=dict(clip_loss=1.0, clip_dense_loss=1.0), world_size=1)
+        run = lambda m, inp: crit(m({"captions": None, **inp}, return_dict=True))[0]
+    return model, run, host_inputs
+
+
+def roofline_probe(config, dev, b, peaks, ms_step, steps, gflop_pair):
+    """CUDA-event time of the dominant kernel at its largest-share launch shape: the 2-CTA tcgen05 GEMM, c_fc + QuickGELU
+    forward of the image tower (ViT configs; the DeCLIP tower sees both views in one 2b-sample pass) or of the text
+    tower (res50)."""
+    import torch
+    from declip_b200 import ops
+    peak, which = (peaks.get("bf16_tflops"), "measured burst (MEASURED_PEAKS.json)") if peaks.get("bf16_tflops") else (
+        1590.0, "fallback (B200_PROFILING.md)")
+    if config == "res50":
+        M, N, K, where = b * 77, 2048, 512, "text c_fc"
+    else:
+        M, N, K, where = b * 50 * (2 if config == "declip" else 1), 3072, 768, "ViT c_fc"
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.zeros(N, device=dev)
+    o1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BF16_GELU, out=o1, out2=o2)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    iters = 20
+    s.record()
+    for _ in range(iters):
+        ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BF16_GELU, out=o1, out2=o2)
+    e.record()
+    torch.cuda.synchronize()
+    kms = s.elapsed_time(e) / iters
+    ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
+    traffic, tsrc = None, "no ncu --set full capture of this launch shape under profiles/ncu_traffic.json"
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = tab.get("gemm_gelu_M%d_N%d_K%d" % (M, N, K))
+        if ent:
+            traffic, tsrc = ent["dram_bytes"], ent["source"]
+    except Exception:
+        pass
+    tf = b * steps / (ms_step * steps / 1e3) * gflop_pair / 1e3
+    return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": traffic, "traffic_source": tsrc,
+            "algorithmic_bytes": 2.0 * (M * K + N * K + 2 * M * N),
+            "kernel": "gemm2_bf16_kernel<K-major,K-major> (cta_group::2) %s+QuickGELU fwd M=%d N=%d K=%d" % (where, M, N, K),
+            "kernel_ms": kms, "peak_source": which,
+            "probe_note": "20 back-to-back launches; the %.0f MB A operand stays in the 126 MB L2 between launches "
+                          "(tensor-bound kernel: DRAM is not the limiter)" % (M * K * 2 / 1e6),
+            "step_mfu": {"achieved_tflops_per_gpu": tf, "train_gflop_per_pair": gflop_pair,
+                         "peak_sustained": peaks.get("bf16_tflops_sustained"),
+                         "frac_of_sustained": tf / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None}}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from declip_b200 import _lib, ops
+    from declip_b200 import _lib
     from declip_b200.dist import DistModule
-    from declip_b200.loss_functions import ClipInfoCELoss
-    from declip_b200.model import model_entry
+    from declip_b200.optim import FusedAdamW
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,30 +380,21 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     b = args.batch
     torch.manual_seed(1234)
-    cfg = dict(type='clip_vitb32', kwargs=dict(
-        image_encode=dict(embed_dim=512),
-        text_encode=dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
-                         embed_dim=512),
-        clip=dict(use_allgather=True)))
-    model = DistModule(model_entry(cfg).to(dev).train())
-    crit = ClipInfoCELoss()
-    from declip_b200.optim import FusedAdamW
+    inner, run, host_inputs = build_workload(args.config, dev, b, world)
+    model = DistModule(inner)
     opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1)
-    # synthetic inputs (pinned host copies for the e2e leg)
     g = torch.Generator().manual_seed(100 + rank)
-    host_imgs = [torch.randn(b, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
-    host_ids = [synthetic_token_ids(b, g).pin_memory() for _ in range(2)]
-    dev_imgs = [h.to(dev) for h in host_imgs]
-    dev_ids = [h.to(dev) for h in host_ids]
+    host = [host_inputs(g) for _ in range(2)]                     # pinned host copies for the e2e leg
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     loss_host = torch.zeros(max(args.steps, 1), dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    def step(images, ids):
-        li, lt = model({"images": images, "captions": None, "token_ids": ids})
-        loss, _ = crit(li, lt)
+    def step(inp):
+        loss = run(model, inp)
         (loss / world).backward()                      # clip_solver.py:418
         model.sync_gradients()                         # dist.py:76-83
         opt.step()
-        model.module.logit_scale.data.clamp_(3.0, 6.0)  # grad_clip config: logit_scale param clamp, clip_solver.py:507-522
+        inner.logit_scale.data.clamp_(3.0, 6.0)        # grad_clip config: logit_scale param clamp, clip_solver.py:507-522
         opt.zero_grad(set_to_none=True)
         return loss
 
@@ -255,11 +417,10 @@ def run_native(args):
 
     def loop_resident(k):
         for i in range(k):
-            step(dev_imgs[i % 2], dev_ids[i % 2])
+            step(resident[i % 2])
 
     copy_stream = torch.cuda.Stream()
-    stage_imgs = [torch.empty_like(dev_imgs[0]) for _ in range(2)]
-    stage_ids = [torch.empty_like(dev_ids[0]) for _ in range(2)]
+    stage = [{k: torch.empty_like(v) for k, v in resident[0].items()} for _ in range(2)]
 
     def loop_e2e(k):
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -271,8 +432,8 @@ def run_native(args):
             with torch.cuda.stream(copy_stream):
                 if i >= 2:
                     copy_stream.wait_event(done[s])
-                stage_imgs[s].copy_(host_imgs[s], non_blocking=True)
-                stage_ids[s].copy_(host_ids[s], non_blocking=True)
+                for key, v in host[s].items():
+                    stage[s][key].copy_(v, non_blocking=True)
                 ready[s].record(copy_stream)
         upload(0)
         for i in range(k):
@@ -280,13 +441,13 @@ def run_native(args):
             if i + 1 < k:
                 upload(i + 1)
             main.wait_event(ready[s])
-            loss = step(stage_imgs[s], stage_ids[s])
+            loss = step(stage[s])
             done[s].record(main)
             loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
-    log("model + inputs ready; warm-up")
+    log("%s: model + inputs ready; warm-up" % args.config)
     for _ in range(max(args.warmup, 3)):
-        step(dev_imgs[0], dev_ids[0])
+        step(resident[0])
     torch.cuda.synchronize()
     log("warm-up done; timing %d resident steps" % args.steps)
     sampler = ClockSampler(local) if rank == 0 else None
@@ -304,10 +465,9 @@ def run_native(args):
         log("timing e2e")
         ms_e2e = timed(loop_e2e, args.steps)
         e2e = {"value": world * b * args.steps / (ms_e2e / 1e3), "unit": "pairs/s",
-               "h2d_bytes_per_step": host_imgs[0].numel() * 4 + host_ids[0].numel() * 8, "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / args.steps, "last_loss": float(loss_host[args.steps - 1])}
-
-    # ---- roofline of the dominant kernel: the tcgen05 GEMM, at its largest-share launch shape (ViT c_fc forward)
+    gflop_pair = train_gflop_per_pair(args.config, world * b)
     roof = None
     if rank == 0:
         peaks = {}
@@ -315,48 +475,17 @@ def run_native(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak, which = (peaks.get("bf16_tflops"), "measured burst (MEASURED_PEAKS.json)") if peaks.get("bf16_tflops") else (
-            1590.0, "fallback (B200_PROFILING.md)")
-        M, N, K = b * 50, 3072, 768
-        a = torch.randn(M, K, device=dev).bfloat16()
-        w = torch.randn(N, K, device=dev).bfloat16()
-        bias = torch.zeros(N, device=dev)
-        o1 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        o2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BF16_GELU, out=o1, out2=o2)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        iters = 20
-        s.record()
-        for _ in range(iters):
-            ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BF16_GELU, out=o1, out2=o2)
-        e.record()
-        torch.cuda.synchronize()
-        kms = s.elapsed_time(e) / iters
-        ach = 2.0 * M * N * K / (kms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # DRAM bytes of this launch shape from the ncu --set full capture (profiles/r01_ncu_gemm_gelu_v7.md:
-                # dram read 44.3 MB + write 260.3 MB at b=512; algorithmic 44.0 + 314.6 MB, part of the output is still
-                # in L2 at kernel end) scaled to the batch in use
-                "traffic": 304.6e6 * (b / 512.0),
-                "kernel": "gemm2_bf16_kernel<K-major,K-major> (cta_group::2) c_fc+QuickGELU fwd M=%d N=%d K=%d" % (M, N, K),
-                "kernel_ms": kms, "peak_source": which,
-                "step_mfu": {"achieved_tflops_per_gpu": b * args.steps / (ms / 1e3) * TRAIN_GFLOP_PER_PAIR / 1e3,
-                             "peak_sustained": peaks.get("bf16_tflops_sustained"),
-                             "frac_of_sustained": (b * args.steps / (ms / 1e3) * TRAIN_GFLOP_PER_PAIR / 1e3) /
-                             peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None}}
-
+        roof = roofline_probe(args.config, dev, b, peaks, ms / args.steps, args.steps, gflop_pair)
     log("roofline probe done")
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # separate process: its thread pool / a slow host cannot stall or perturb the GPU arm
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
-                                "--warmup", "1"], capture_output=True, text=True, timeout=240)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                "--steps", "5", "--warmup", "1"], capture_output=True, text=True, timeout=420)
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as ex:   # reported, never silently dropped
-            cpu = {"value": None, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": None, "unit": "pairs/s", "cores": one_socket_cores(), "kind": "reference",
                    "sample": "cpu baseline leg failed: %r" % (ex,)}
         log("cpu baseline done")
 
@@ -365,10 +494,11 @@ def run_native(args):
             "metric": "image-text pairs/sec", "value": world * b * args.steps / (ms / 1e3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CLIP ViT-B/32 + 12L text transformer training step: fwd + ClipInfoCELoss + bwd + "
-                                   "grad all-reduce + AdamW (BASELINE configs[1], per-GPU batch %d)" % b,
-                       "global_batch": world * b, "seq_len": 77, "image": "3x224x224 fp32", "parallelism": "dp%d" % world,
-                       "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch)", "l2": "inputs+activations >> 126 MB L2 (no flush needed)"},
+            "config": {"workload": WORKLOAD_TEXT[args.config] + ", per-GPU batch %d" % b, "name": args.config,
+                       "global_batch": world * b, "seq_len": 77,
+                       "image": "%dx224x224 fp32" % (6 if args.config in ("declip", "filip") else 3),
+                       "parallelism": "dp%d" % world, "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch, "
+                       "rewrites the bf16 GEMM shadows)", "l2": "inputs+activations >> 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

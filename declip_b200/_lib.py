@@ -107,6 +107,7 @@ SIGNATURES = {
     "dc_bpe_token_id": (c_int, [c_void_p, ctypes.c_char_p]),
     "dc_bpe_encode": (c_ll, [c_void_p, ctypes.c_char_p, c_void_p, c_ll]),
     "dc_bpe_tokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
+    "dc_bpe_tokenize_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),

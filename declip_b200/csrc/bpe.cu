@@ -10,6 +10,7 @@
 #include <strings.h>
 
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -73,7 +74,7 @@ struct Bpe {
   std::unordered_map<std::string, int> encoder;            // token string -> id
   std::unordered_map<std::string, int> ranks;              // "first\x01second" -> merge rank
   int sot = -1, eot = -1, mask = -1;
-  std::mutex mu;
+  std::shared_mutex mu;   // cache hits (the steady state) only take the shared side
   std::unordered_map<std::string, std::vector<int>> cache; // byte-encoded word -> ids
 
   // simple_tokenizer.py:16-37
@@ -142,7 +143,7 @@ struct Bpe {
   // simple_tokenizer.py:85-122 on the byte-encoded word `syms` (one stand-in per byte); appends the ids
   bool bpe_word(const std::string& key, std::vector<std::string>& w, std::vector<int>& out) {
     {
-      std::lock_guard<std::mutex> lk(mu);
+      std::shared_lock<std::shared_mutex> lk(mu);
       auto it = cache.find(key);
       if (it != cache.end()) { out.insert(out.end(), it->second.begin(), it->second.end()); return true; }
     }
@@ -171,7 +172,7 @@ struct Bpe {
       ids.push_back(it->second);
     }
     out.insert(out.end(), ids.begin(), ids.end());
-    std::lock_guard<std::mutex> lk(mu);
+    std::unique_lock<std::shared_mutex> lk(mu);
     if (cache.size() < (1u << 20)) cache.emplace(key, std::move(ids));
     return true;
   }
@@ -266,8 +267,26 @@ long long dc_bpe_encode(dc_bpe_t* h, const char* text, int* ids_out, long long c
   return n;
 }
 
+// basic_clean + whitespace_clean + lower (simple_tokenizer.py:53-63,126) for a caption the caller has classified as
+// printable ASCII without '&' (no entity to unescape, nothing for ftfy to repair): strip, collapse blanks, lower-case.
+static void clean_printable_ascii(const char* t, std::string& out) {
+  out.clear();
+  bool pending_space = false;
+  for (const char* p = t; *p; ++p) {
+    const char c = *p;
+    if (c == ' ') { pending_space = !out.empty(); continue; }
+    if (pending_space) { out.push_back(' '); pending_space = false; }
+    out.push_back((c >= 'A' && c <= 'Z') ? static_cast<char>(c + 32) : c);
+  }
+}
+
 int dc_bpe_tokenize(dc_bpe_t* h, const char* const* texts, int n, int context_length, long long* ids, int* lengths,
                     int threads) {
+  return dc_bpe_tokenize_ex(h, texts, nullptr, n, context_length, ids, lengths, threads);
+}
+
+int dc_bpe_tokenize_ex(dc_bpe_t* h, const char* const* texts, const unsigned char* raw_ascii, int n, int context_length,
+                       long long* ids, int* lengths, int threads) {
   if (h == nullptr || texts == nullptr || ids == nullptr) return dc::set_error("bpe: null argument");
   if (context_length < 2) return dc::set_error("bpe: context_length must be at least 2");
   if (threads < 1) threads = 1;
@@ -275,10 +294,13 @@ int dc_bpe_tokenize(dc_bpe_t* h, const char* const* texts, int n, int context_le
   std::vector<int> status(threads, 0);
   auto work = [&](int t) {
     std::vector<int> tok;
+    std::string cleaned;
     for (int i = t; i < n; i += threads) {
       tok.clear();
       tok.push_back(h->impl.sot);
-      if (!h->impl.encode(texts[i], tok)) { status[t] = 1; return; }
+      const char* text = texts[i];
+      if (raw_ascii != nullptr && raw_ascii[i]) { clean_printable_ascii(text, cleaned); text = cleaned.c_str(); }
+      if (!h->impl.encode(text, tok)) { status[t] = 1; return; }
       tok.push_back(h->impl.eot);
       long long* row = ids + static_cast<long long>(i) * context_length;
       int len = static_cast<int>(tok.size());

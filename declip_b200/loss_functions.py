@@ -136,3 +136,93 @@ class NT_Xent_gather(_Loss):
         labels = torch.cat((lab + l_bs, lab))                             # positives: nt_xent.py:77-78
         skip = torch.cat((lab, lab + l_bs))                               # self columns: nt_xent.py:80,83
         return F_.MaskedRowCE.apply(sim, labels.long(), skip.int(), 2 * bs)
+
+
+class DeclipCriterion(torch.nn.Module):
+    """The DeCLIP solver's loss composition, prototype/solver/declip_solver.py:435-533, as one callable on the
+    `return_dict=True` output of DECLIP.forward: four ClipInfoCELoss terms averaged (image_text_two_view) or two
+    (only_image_two_view), MLM, nearest-neighbour text supervision, SimSiam, each divided by world size and combined
+    with `clip_simsiam_loss_weight` (yfcc15m_vit_declip/config.yaml:28-32).  NTXentLoss is evaluated lazily: the
+    reference computes it every step but it only enters the loss when the weight type is 'convirt'."""
+
+    DEFAULT_WEIGHTS = dict(clip_loss=0.4, simsiam_loss=0.2, masking_language=0.2, nn_text=0.2)
+
+    def __init__(self, weights=None, image_text_two_view=True, world_size=None):
+        super().__init__()
+        self.weights = dict(weights or self.DEFAULT_WEIGHTS)
+        self.image_text_two_view = image_text_two_view
+        self.world_size = world_size
+        self.criterion = ClipInfoCELoss()
+        self.simsiam_criterion = SimsiamLoss()
+
+    def forward(self, out, curr_step=0, total_step=1):
+        world = self.world_size if self.world_size is not None else F_.dist_info()[1]
+        crit, w = self.criterion, self.weights
+        li1, li2, lt1, lt2 = out['logits']
+        clip_1, target = crit(li1, lt1)
+        stats = dict(crit.stats)                        # prec@1/5 are logged on the first pair (declip_solver.py:535-536)
+        clip_2, _ = crit(li2, lt2)
+        if self.image_text_two_view:
+            li1a, li2a, lt1a, lt2a = out['logits_aug']
+            clip = (clip_1 + clip_2 + crit(li1a, lt1a)[0] + crit(li2a, lt2a)[0]) / 4
+        else:
+            clip = (clip_1 + clip_2) / 2
+        clip = clip / world
+        zero = torch.zeros_like(clip)
+        mlm = out['text_self_supervised'] / world if 'text_self_supervised' in out else zero
+        if 'nn_text_logits' in out:
+            n1, n2, n1a, n2a = out['nn_text_logits']
+            nn_text = (crit(n1, n1a)[0] + crit(n2, n2a)[0]) / 2 / world
+        else:
+            nn_text = zero
+        p1, p2, z1, z2 = out['simsiam_features']
+        simsiam = self.simsiam_criterion(p1, z1, p2, z2) / world
+        parts = dict(clip=clip, mlm=mlm, nn=nn_text, simsiam=simsiam)
+        kind = w.get('type', None)
+        if not kind:
+            loss = clip * w['clip_loss']
+            if w.get('simsiam_loss', 0):
+                loss = loss + simsiam * w['simsiam_loss']
+            if w.get('masking_language', 0):
+                loss = loss + mlm * w['masking_language']
+            if w.get('nn_text', 0):
+                loss = loss + nn_text * w['nn_text']
+        elif kind == 'convirt':
+            tf, f1, f2 = out['features']
+            ntx = NTXentLoss(f1.shape[0])
+            parts['nt_xent'] = (ntx(f1, tf) + ntx(f2, tf)) / world
+            loss = (clip + parts['nt_xent']) / 2 * w['clip_loss'] + simsiam * w['simsiam_loss']
+        elif kind == 'linear':
+            cw = 0.2 + 0.8 * curr_step / total_step
+            loss = clip * cw + simsiam * (1.0 - cw)
+        elif kind == 'shift':
+            loss = clip if curr_step % 2 == 0 else simsiam
+        else:
+            raise NotImplementedError("clip_simsiam_loss_weight.type %r" % kind)
+        crit.stats = stats
+        return loss, parts, target
+
+    def accuracy(self):
+        return self.criterion.accuracy()
+
+
+class FilipCriterion(torch.nn.Module):
+    """prototype/solver/filip_solver.py:436-520: ClipInfoCELoss on the global logits and on the token-wise
+    `dense_logits`, weights clip_loss / clip_dense_loss (yfcc15m_vit_filip/config.yaml:33-35: 0.0 / 1.0)."""
+
+    def __init__(self, weights=None, world_size=None):
+        super().__init__()
+        self.weights = dict(weights or dict(clip_loss=0.0, clip_dense_loss=1.0))
+        self.world_size = world_size
+        self.criterion = ClipInfoCELoss()
+
+    def forward(self, out):
+        world = self.world_size if self.world_size is not None else F_.dist_info()[1]
+        dense, target = self.criterion(*out['dense_logits'])
+        dense = dense / world
+        loss = dense * self.weights['clip_dense_loss']
+        parts = dict(dense=dense)
+        if self.weights.get('clip_loss', 0):
+            parts['clip'] = self.criterion(*out['logits'])[0] / world
+            loss = loss + parts['clip'] * self.weights['clip_loss']
+        return loss, parts, target

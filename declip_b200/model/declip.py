@@ -90,7 +90,12 @@ class DECLIP(CLIP):
         self.return_simsiam_nn_text = return_simsiam_nn_text
         self.text_mask_type = text_mask_type
         self.EDA = EDA
+        if forward_type not in ('split', 'image_concat'):
+            raise NotImplementedError("declip_b200: forward_type %r (declip.py:225-232 knows 'split' / 'image_concat')" % (forward_type,))
         self.forward_type = forward_type
+        if self.EDA:
+            from ..eda import EDA as _EDA
+            self.emd = _EDA()                                                                      # declip.py:154-155
         if text_mask_type is not None:
             enc_dim = self.encode_text.text_projection.weight.shape[-1]
             self.text_label_predictor = nn.Linear(enc_dim, self.encode_text.vocab_size)
@@ -117,11 +122,29 @@ class DECLIP(CLIP):
             ids = input['token_ids']
             return ids, input.get('token_ids_aug', ids), input.get('mlm')
         texts = self.sample_captions(input['captions'])
-        if self.EDA:
-            raise NotImplementedError("declip_b200: EDA text augmentation on strings needs `textaugment`; pass "
-                                      "token_ids / token_ids_aug instead")
         ids = self.encode_text.tokenize(texts)
-        return ids, ids, None
+        if not self.EDA:
+            if self.text_mask_type is not None:
+                raise NotImplementedError('No EDA')                                                 # declip.py:212
+            return ids, ids, None
+        texts_aug = self.emd.augment_batch(texts)                                                   # declip.py:203-211
+        return ids, self.encode_text.tokenize(texts_aug), None
+
+    def _encode_two_views(self, images):
+        """image_features of the two views stacked on the channel axis (declip.py:199,225-232).  The ViT tower has no
+        cross-sample coupling, so both views always go through it as ONE 2B-sample pass — for a contiguous
+        [B,6,H,W] batch that is a zero-copy [2B,3,H,W] view with the views interleaved — whatever `forward_type` says.
+        The ResNet tower's BatchNorm statistics do depend on the grouping: 'image_concat' normalises over 2B samples,
+        'split' over B twice (two passes, running statistics updated twice)."""
+        B = images.shape[0]
+        coupled = any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.visual.modules())
+        if coupled and self.forward_type != 'image_concat':
+            return self.encode_image(images[:, :3]), self.encode_image(images[:, 3:])
+        if images.is_contiguous():
+            both = self.encode_image(images.view(2 * B, 3, images.shape[2], images.shape[3]))
+            return both[0::2], both[1::2]
+        both = self.encode_image(torch.cat([images[:, :3], images[:, 3:]], dim=0))
+        return both[:B], both[B:]
 
     def forward(self, input, return_dict=False):
         if not return_dict:
@@ -129,7 +152,6 @@ class DECLIP(CLIP):
         if not (self.training and self.use_allgather):
             raise NotImplementedError('2-View: Not Implemented')                                    # declip.py:301-302
         images = input['images']
-        images_1, images_2 = images[:, :3], images[:, 3:]                                           # declip.py:199
         ids, ids_aug, mlm = self._text_inputs(input)
         if self.text_mask_type is not None:
             text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
@@ -138,8 +160,7 @@ class DECLIP(CLIP):
         else:
             text_features = self.encode_text(ids)
             text_features_aug = self.encode_text(ids_aug) if self.EDA else text_features.detach()
-        image_features_1 = self.encode_image(images_1)
-        image_features_2 = self.encode_image(images_2)
+        image_features_1, image_features_2 = self._encode_two_views(images)                         # declip.py:199,225-232
         # SimSiam heads                                                                              declip.py:238-241
         z1 = self.projector(image_features_1)
         z2 = self.projector(image_features_2)

@@ -258,6 +258,11 @@ long long dc_bpe_encode(dc_bpe_t* h, const char* text, int* ids_out, long long c
  * padded; lengths[n] (optional) = tokens written per row. */
 int dc_bpe_tokenize(dc_bpe_t* h, const char* const* texts, int n, int context_length, long long* ids, int* lengths,
                     int threads);
+/* As above; raw_ascii[i] != 0 marks a caption the caller has NOT cleaned but knows to be printable ASCII without '&'
+ * (str.isascii() and str.isprintable()): the library strips it, collapses blanks and lower-cases it itself — the whole of
+ * basic_clean / whitespace_clean / lower for such text — so the host spends no per-caption Python time on it. */
+int dc_bpe_tokenize_ex(dc_bpe_t* h, const char* const* texts, const unsigned char* raw_ascii, int n, int context_length,
+                       long long* ids, int* lengths, int threads);
 
 /* ------------------------------------------------------------------ composite encoders (C++ executors)
  * One call runs a whole tower forward (or backward) as a fixed launch sequence on `stream`.

@@ -12,7 +12,19 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("DECLIP_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py
+
+
+def _resolve_root():
+    env = os.environ.get("DECLIP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/prototype"):
+        return "/root/reference"
+    return _STAGED          # GPU box: the unmodified modules staged by oracle/build_ref.py
+
+
+REF_ROOT = _resolve_root()
 
 
 def available():
@@ -38,8 +50,11 @@ def _fake_bpe():
     return _bpe_path
 
 
-def setup():
+def setup(force_cpu=False):
     global _ready
+    if force_cpu and torch.cuda.is_available():
+        # CPU arm on a GPU box: the reference's hard-coded .cuda() calls must stay on the host
+        torch.Tensor.cuda = lambda self, *a, **k: self
     if _ready:
         return
     if not available():
@@ -262,3 +277,74 @@ def reference_clip_res_step(sd, images, ids, embed_dim=1024, layers=(3, 4, 6, 3)
     return {"loss": loss.detach(), "logits_per_image": li.detach(),
             "grads": {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None},
             "stats": {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k}}, model
+
+
+class Stepper:
+    """One persistent reference model + synthetic batch for timing (bench.py --impl reference / cpu_baseline): the
+    UNMODIFIED reference modules, built once; `step()` = zero_grad + forward + the solver's loss + backward, CPU fp32.
+    config in {'clip', 'declip', 'filip', 'res50'} (BASELINE configs[1..4] at a bounded sample batch)."""
+
+    def __init__(self, config, batch, seed=0):
+        from . import golden, synth
+        setup(force_cpu=True)
+        from prototype.model import model_entry
+        self.config, self.batch = config, batch
+        tcfg = dict(bpe_path=_fake_bpe(), text_encode_type="Transformer", text_model_utils=dict(random=False, freeze=False))
+        B = batch
+        if config == "clip":
+            sd = synth.clip_vit_state_dict(seed=seed)
+            cfg = dict(type="clip_vitb32", kwargs=dict(image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **tcfg),
+                                                       clip=dict(use_allgather=False)))
+            images, ids = synth.synth_images(B, seed=seed), synth.synth_token_ids(B, seed=seed)
+            tok = lambda texts, context_length=77, return_length=False, mask_type=None: ids
+        elif config == "res50":
+            sd = synth.clip_res_state_dict(seed=seed)
+            cfg = dict(type="clip_res50", kwargs=dict(image_encode=dict(embed_dim=1024, use_sync_bn=False, bn_group_size=1),
+                                                      text_encode=dict(embed_dim=1024, **tcfg), clip=dict(use_allgather=False)))
+            images, ids = synth.synth_images(B, seed=seed), synth.synth_token_ids(B, seed=seed)
+            tok = lambda texts, context_length=77, return_length=False, mask_type=None: ids
+        elif config == "declip":
+            _ensure_pg()
+            c = dict(batch=B, v_layers=12, t_layers=12, embed_dim=512, seed=seed, nn_size=65536)
+            sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(c)
+            cfg = dict(type="declip_vitb32", kwargs=dict(
+                image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **tcfg),
+                clip=dict(use_allgather=True, text_mask_type="MLM", return_nn_bank=True, feature_dim=512, nn_size=65536)))
+            tok = lambda texts, context_length=77, return_length=False, mask_type=None: (
+                (mlm_ids.clone(), mlm_labels.clone()) if mask_type is not None else ids_aug)
+            self._bank = bank
+        elif config == "filip":
+            _ensure_pg()
+            c = dict(batch=B, v_layers=12, t_layers=12, embed_dim=768, seed=seed)
+            sd, images, mlm_ids, mlm_labels = golden.filip_inputs(c)
+            cfg = dict(type="filip_vitb32", kwargs=dict(
+                image_encode=dict(embed_dim=768), text_encode=dict(embed_dim=768, **tcfg),
+                clip=dict(use_allgather=True, text_mask_type="MLM", return_dense=True, select_topk=True, feature_dim=768,
+                          mask_rate=0.5, patch_number=14)))
+            tok = lambda texts, context_length=77, return_length=False, mask_type=None: (
+                (mlm_ids.clone(), mlm_labels.clone()) if mask_type is not None else mlm_ids)
+        else:
+            raise ValueError(config)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):          # the reference prints banners while building
+            self.model = model_entry(cfg).train()
+        self.model.load_state_dict(sd, strict=True)
+        self.model.encode_text.tokenize = tok
+        if config == "declip":
+            self.model.nn_replacer_text.bank = self._bank.clone()
+            self.model.nn_replacer_text.bank_ptr = torch.LongTensor([0])
+        self.images = images
+        self.crit = clip_loss_fn()
+
+    def step(self):
+        from . import declip_ref, filip_ref
+        self.model.zero_grad(set_to_none=True)
+        batch = {"images": self.images, "captions": [["x"]] * self.batch}
+        if self.config in ("clip", "res50"):
+            loss, _ = self.crit(*self.model(batch))
+        elif self.config == "declip":
+            loss, _ = declip_ref.declip_loss(self.model(batch, return_dict=True), declip_ref.LOSS_WEIGHTS)
+        else:
+            loss, _ = filip_ref.filip_loss(self.model(batch, return_dict=True), filip_ref.LOSS_WEIGHTS)
+        loss.backward()
+        return loss.item()

@@ -1,0 +1,208 @@
+"""Shared runners for the golden-vector parity cases (used by tests/test_gpu_fullsize.py and tools/parity_report.py):
+each builds the drop-in model for a golden case, runs one training step through the C ABI on `dev`, and returns the
+measured distances from the reference's own outputs as a flat dict.  The tolerances the tests assert are TOL below
+(about 3x the worst value measured on B200, tools/parity_report.py -> profiles/r02_parity_report.json)."""
+import torch
+
+
+def cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-20)).item()
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def grad_metrics(model, g, zero_norm=1e-6):
+    """Per-parameter cosine (on the golden's strided sample) and norm ratio; parameters whose reference gradient is
+    exactly zero up to round-off (biases feeding a BatchNorm) must be numerically zero here as well."""
+    from oracle import golden
+    params = dict(model.named_parameters())
+    have = set(k for k, p in params.items() if p.grad is not None)
+    rows, zero_max, sparse = [], 0.0, []
+    for k, ref in g["grads"].items():
+        mine = params[k].grad.detach().float().reshape(-1).cpu()
+        nr = mine.norm().item() / (ref["norm"] + 1e-20)
+        if ref["norm"] < zero_norm:
+            zero_max = max(zero_max, mine.abs().max().item())
+            continue
+        if (ref["sample"] != 0).sum().item() < 16:
+            sparse.append((nr, k))       # sparse (token embedding at small batch) or scalar: norm only
+            continue
+        rows.append((cos(mine[golden.sample_index(mine.numel())], ref["sample"]), nr, k))
+    rows.sort()
+    big = [r for r in rows if "weight" in r[2] and "ln_" not in r[2] and "bn" not in r[2]]
+    return {
+        "grad_keys_match": have == set(g["grads"]),
+        "grad_cos_min": rows[0][0], "grad_cos_min_name": rows[0][2],
+        "grad_cos_p10": rows[len(rows) // 10][0],
+        "grad_cos_min_matrices": min(r[0] for r in big) if big else 1.0,
+        "grad_norm_ratio_min": min(r[1] for r in rows), "grad_norm_ratio_max": max(r[1] for r in rows),
+        "grad_sparse_norm_ratio_min": min([s[0] for s in sparse], default=1.0),
+        "grad_sparse_norm_ratio_max": max([s[0] for s in sparse], default=1.0),
+        "grad_zero_max_abs": zero_max,
+        "worst": ["cos %.5f normratio %.4f %s" % r for r in rows[:8]],
+    }
+
+
+def _text_cfg(c, embed):
+    return dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
+                embed_dim=embed, transformer_layers=c["t_layers"])
+
+
+def run_clip(name, dev):
+    from declip_b200.loss_functions import ClipInfoCELoss
+    from declip_b200.model import model_entry
+    from oracle import golden, synth
+    g = golden.load(name)
+    c = g["case"]
+    model = model_entry(dict(type='clip_vitb32', kwargs=dict(image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]),
+                                                             text_encode=_text_cfg(c, c["embed_dim"]),
+                                                             clip=dict(use_allgather=False))))
+    sd = synth.clip_vit_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], v_layers=c["v_layers"], t_layers=c["t_layers"])
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    images = synth.synth_images(c["batch"], seed=c["seed"]).to(dev)
+    ids = synth.synth_token_ids(c["batch"], seed=c["seed"]).to(dev)
+    with torch.no_grad():
+        fi, ft = model.encode_image(images), model.encode_text(ids)
+    li, lt = model({"images": images, "captions": None, "token_ids": ids})
+    crit = ClipInfoCELoss()
+    loss, labels = crit(li, lt)
+    loss.backward()
+    torch.cuda.synchronize()
+    m = {"loss": loss.item(), "loss_ref": g["loss"], "dloss": abs(loss.item() - g["loss"]),
+         "labels_equal": bool(torch.equal(labels.cpu(), g["labels"])),
+         "feat_i_cos_min": torch.nn.functional.cosine_similarity(fi.cpu(), g["image_features"], dim=1).min().item(),
+         "feat_t_cos_min": torch.nn.functional.cosine_similarity(ft.cpu(), g["text_features"], dim=1).min().item(),
+         "logits_cos": min(cos(li.cpu(), g["logits_per_image"]), cos(lt.cpu(), g["logits_per_text"])),
+         "logits_max_abs": max((li.cpu() - g["logits_per_image"]).abs().max().item(),
+                               (lt.cpu() - g["logits_per_text"]).abs().max().item()),
+         "conv1_frozen": dict(model.named_parameters())["visual.conv1.weight"].grad is None}
+    m.update(grad_metrics(model, g))
+    return m
+
+
+def declip_loss(out, world=1):
+    """declip_solver.py:435-517 with the drop-in loss classes of this repo (also shipped as
+    declip_b200.loss_functions.declip_criterion — this copy keeps the test independent of it)."""
+    from declip_b200.loss_functions import ClipInfoCELoss, NTXentLoss, SimsiamLoss
+    from oracle.declip_ref import LOSS_WEIGHTS as W
+    crit, ss, ntx = ClipInfoCELoss(), SimsiamLoss(), NTXentLoss(out["features"][0].shape[0])
+    li1, li2, lt1, lt2 = out["logits"]
+    li1a, li2a, lt1a, lt2a = out["logits_aug"]
+    clip = (crit(li1, lt1)[0] + crit(li2, lt2)[0] + crit(li1a, lt1a)[0] + crit(li2a, lt2a)[0]) / 4 / world
+    mlm = out["text_self_supervised"] / world
+    n1, n2, n1a, n2a = out["nn_text_logits"]
+    nn_ = (crit(n1, n1a)[0] + crit(n2, n2a)[0]) / 2 / world
+    p1, p2, z1, z2 = out["simsiam_features"]
+    sim = ss(p1, z1, p2, z2) / world
+    tf, f1, f2 = out["features"]
+    nt = (ntx(f1, tf) + ntx(f2, tf)) / world
+    loss = clip * W["clip_loss"] + sim * W["simsiam_loss"] + mlm * W["masking_language"] + nn_ * W["nn_text"]
+    return loss, dict(clip=clip, mlm=mlm, nn=nn_, simsiam=sim, nt_xent=nt)
+
+
+def build_declip(c, dev):
+    from declip_b200.model import model_entry
+    from oracle import golden
+    cfg = dict(type='declip_vitb32', kwargs=dict(
+        image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]), text_encode=_text_cfg(c, c["embed_dim"]),
+        clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=c["embed_dim"],
+                  nn_size=c["nn_size"])))
+    model = model_entry(cfg)
+    sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(c)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    model.nn_replacer_text.load_bank(bank, dev)
+    batch = {"images": images.to(dev), "token_ids": mlm_ids.to(dev), "token_ids_aug": ids_aug.to(dev),
+             "mlm": (mlm_ids.to(dev), mlm_labels)}
+    return model, batch
+
+
+def run_declip(name, dev):
+    from oracle import golden
+    g = golden.load(name)
+    model, batch = build_declip(g["case"], dev)
+    out = model(batch, return_dict=True)
+    loss, parts = declip_loss(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    m = {"loss": loss.item(), "loss_ref": g["loss"], "dloss": abs(loss.item() - g["loss"])}
+    for k, v in g["parts"].items():
+        m["d_" + k] = abs(parts[k].item() - v)
+    m["logits_cos"] = min(cos(a.cpu(), b) for key in ("logits", "logits_aug", "nn_text_logits") for a, b in zip(out[key], g[key]))
+    m["features_cos_min"] = min(torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item()
+                                for a, b in zip(out["features"], g["features"]))
+    m["simsiam_features_cos"] = min(cos(a.cpu(), b) for a, b in zip(out["simsiam_features"], g["simsiam_features"]))
+    m.update(grad_metrics(model, g))
+    sd = model.state_dict()
+    m["bn_stats_rel_max"] = max(rel(sd[k].cpu(), v) for k, v in g["stats"].items() if v.dtype.is_floating_point)
+    m["bank_ptr_equal"] = model.nn_replacer_text.bank_ptr == g["bank_ptr"]
+    m["bank_tail_cos"] = cos(model.nn_replacer_text.bank[:2 * g["case"]["batch"]].t().cpu(), g["bank_tail"])
+    return m
+
+
+def run_filip(name, dev):
+    from declip_b200.loss_functions import ClipInfoCELoss
+    from declip_b200.model import model_entry
+    from oracle import golden
+    from oracle.filip_ref import LOSS_WEIGHTS as W
+    g = golden.load(name)
+    c = g["case"]
+    cfg = dict(type='filip_vitb32', kwargs=dict(
+        image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]), text_encode=_text_cfg(c, c["embed_dim"]),
+        clip=dict(use_allgather=True, text_mask_type='MLM', return_dense=True, select_topk=True, feature_dim=c["embed_dim"],
+                  mask_rate=0.5, patch_number=14)))
+    model = model_entry(cfg)
+    sd, images, mlm_ids, mlm_labels = golden.filip_inputs(c)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    out = model({"images": images.to(dev), "token_ids": mlm_ids.to(dev), "mlm": (mlm_ids.to(dev), mlm_labels)},
+                return_dict=True)
+    crit = ClipInfoCELoss()
+    clip_loss = crit(*out["logits"])[0]
+    dense_loss = crit(*out["dense_logits"])[0]
+    loss = clip_loss * W["clip_loss"] + dense_loss * W["clip_dense_loss"]
+    loss.backward()
+    torch.cuda.synchronize()
+    m = {"d_clip": abs(clip_loss.item() - g["parts"]["clip"]), "d_dense": abs(dense_loss.item() - g["parts"]["dense"]),
+         "logits_cos": min(cos(a.cpu(), b) for a, b in zip(out["logits"], g["logits"])),
+         "dense_logits_cos": min(cos(a.cpu(), b) for a, b in zip(out["dense_logits"], g["dense_logits"]))}
+    m.update(grad_metrics(model, g))
+    return m
+
+
+def run_res(name, dev):
+    from declip_b200.loss_functions import ClipInfoCELoss
+    from declip_b200.model import model_entry
+    from oracle import golden
+    g = golden.load(name)
+    c = g["case"]
+    cfg = dict(type='clip_res50', kwargs=dict(
+        image_encode=dict(embed_dim=c["embed_dim"], use_sync_bn=False, bn_group_size=1, layers=tuple(c["layers"])),
+        text_encode=_text_cfg(c, c["embed_dim"]), clip=dict(use_allgather=False)))
+    model = model_entry(cfg)
+    sd, images, ids = golden.res_inputs(c)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    li, lt = model({"images": images.to(dev), "captions": None, "token_ids": ids.to(dev)})
+    loss, _ = ClipInfoCELoss()(li, lt)
+    loss.backward()
+    torch.cuda.synchronize()
+    m = {"loss": loss.item(), "loss_ref": g["loss"], "dloss": abs(loss.item() - g["loss"]),
+         "logits_cos": cos(li.cpu(), g["logits_per_image"])}
+    m.update(grad_metrics(model, g, zero_norm=1e-7))
+    sdm = model.state_dict()
+    m["bn_stats_rel_max"] = max(rel(sdm[k].cpu(), v) for k, v in g["stats"].items() if v.dtype.is_floating_point)
+    return m
+
+
+RUNNERS = {
+    "clip_vitb32_l2_b8": run_clip, "clip_vitb32_l12_b32": run_clip, "clip_vitb32_l12_b512": run_clip,
+    "declip_vitb32_l2_b8": run_declip, "declip_vitb32_l12_b64": run_declip,
+    "filip_vitb32_l2_b8": run_filip, "filip_vitb32_l12_b64": run_filip,
+    "clip_res50_l1111_b4": run_res, "clip_res50_l3463_b32": run_res,
+}
