@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="clip", choices=["clip", "declip", "filip", "res50"])
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--head", default="strips", choices=["fused", "strips"],
+                    help="clip / res50: fused = csrc/head.cu (no [b,N] strip in HBM); strips = compat path returning logits")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -268,7 +270,7 @@ def synthetic_token_ids(batch, gen, ctx=77):
     return ids
 
 
-def build_workload(config, dev, b, world):
+def build_workload(config, dev, b, world, head="strips"):
     """(model, loss_fn(model_out) -> scalar loss, host-input factory, inputs -> model input dict)."""
     import torch
     from declip_b200.loss_functions import ClipInfoCELoss, DeclipCriterion, FilipCriterion
@@ -276,10 +278,11 @@ def build_workload(config, dev, b, world):
     text = dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False))
     if config == "clip":
         cfg = dict(type='clip_vitb32', kwargs=dict(image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **text),
-                                                   clip=dict(use_allgather=True)))
+                                                   clip=dict(use_allgather=True, fused_head=head == "fused")))
     elif config == "res50":
         cfg = dict(type='clip_res50', kwargs=dict(image_encode=dict(embed_dim=1024, use_sync_bn=False, bn_group_size=1),
-                                                  text_encode=dict(embed_dim=1024, **text), clip=dict(use_allgather=True)))
+                                                  text_encode=dict(embed_dim=1024, **text),
+                                                  clip=dict(use_allgather=True, fused_head=head == "fused")))
     elif config == "declip":
         cfg = dict(type='declip_vitb32', kwargs=dict(
             image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **text),
@@ -380,7 +383,7 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     b = args.batch
     torch.manual_seed(1234)
-    inner, run, host_inputs = build_workload(args.config, dev, b, world)
+    inner, run, host_inputs = build_workload(args.config, dev, b, world, args.head)
     model = DistModule(inner)
     opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1)
     g = torch.Generator().manual_seed(100 + rank)
@@ -497,7 +500,8 @@ def run_native(args):
             "config": {"workload": WORKLOAD_TEXT[args.config] + ", per-GPU batch %d" % b, "name": args.config,
                        "global_batch": world * b, "seq_len": 77,
                        "image": "%dx224x224 fp32" % (6 if args.config in ("declip", "filip") else 3),
-                       "parallelism": "dp%d" % world, "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch, "
+                       "parallelism": "dp%d" % world, "head": args.head if args.config in ("clip", "res50") else "strips",
+                       "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch, "
                        "rewrites the bf16 GEMM shadows)", "l2": "inputs+activations >> 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }

@@ -46,6 +46,13 @@ class TowerCfg(ctypes.Structure):
     ]
 
 
+class HeadArgs(ctypes.Structure):
+    _fields_ = [("b", c_int), ("n", c_int), ("e", c_int), ("ld", c_int), ("n_src", c_int), ("row0", c_int),
+                ("x_off", c_int * 2), ("y_off", c_int * 2), ("cross", c_int), ("ld_strip", c_int),
+                ("x_base", c_void_p), ("y_src", c_void_p * 8), ("ws", c_void_p),
+                ("strips", c_void_p * 2)]
+
+
 class AdamWEntry(ctypes.Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("shadow", c_void_p), ("numel", c_ull), ("group", c_int), ("reserved", c_int)]
@@ -107,6 +114,11 @@ SIGNATURES = {
     "dc_bpe_token_id": (c_int, [c_void_p, ctypes.c_char_p]),
     "dc_bpe_encode": (c_ll, [c_void_p, ctypes.c_char_p, c_void_p, c_ll]),
     "dc_bpe_tokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
+    "dc_head_workspace_floats": (c_size_t, [c_int, c_int]),
+    "dc_head_layout": (c_int, [c_int, c_int, c_void_p]),
+    "dc_head_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "dc_head_forward": (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
+    "dc_head_backward": (c_int, [ctypes.POINTER(HeadArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_bpe_tokenize_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
     "dc_tower_workspace_bytes": (c_size_t, [ctypes.POINTER(TowerCfg)]),
     "dc_vit_forward": (c_int, [ctypes.POINTER(TowerCfg), c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -695,3 +695,134 @@ class MaskedRowCE(torch.autograd.Function):
                                        _PTR(skip.data_ptr()), _PTR(lse.data_ptr()), _PTR(g.data_ptr()), 1.0 / ctx.denom,
                                        _PTR(d.data_ptr()), d.stride(0), 1, _stream()), "dc_ce_strip_bwd")
         return d, None, None, None
+
+
+# =====================================================================================================================
+# Fused distributed contrastive head (csrc/head.cu): normalise -> [gather] -> strips + ClipInfoCELoss + accuracy, and the
+# whole backward, in three launches; no [b, N] strip in HBM.  clip.py:129-146, loss.py:40-50, misc.py:415-428.
+# =====================================================================================================================
+class HeadLayout:
+    """Float offsets into the head workspace (dc_head_layout)."""
+
+    _cache = {}
+
+    def __init__(self, lib, b, e):
+        arr = (ctypes.c_longlong * 8)()
+        _lib.check(lib.dc_head_layout(b, e, arr), "dc_head_layout")
+        self.out, self.lse, self.g, self.alab, self.ea, self.cnt, self.dxn, self.total = list(arr)
+
+    @classmethod
+    def get(cls, lib, b, e):
+        key = (b, e)
+        if key not in cls._cache:
+            cls._cache[key] = cls(lib, b, e)
+        return cls._cache[key]
+
+
+def head_args(b, n, e, ld, row0, x_base, y_srcs, ws, x_off=(0, None), y_off=(None, 0), cross=True, strips=None):
+    """dc_head_args for the symmetric pair: direction 0 = image rows x text columns, direction 1 = the transpose; the image
+    feature sits at columns [0, e) of a row, the text feature at [e, 2e) unless offsets are given."""
+    a = _lib.HeadArgs()
+    a.b, a.n, a.e, a.ld, a.n_src, a.row0 = b, n, e, ld, len(y_srcs), row0
+    xo = (x_off[0], e if x_off[1] is None else x_off[1])
+    yo = (e if y_off[0] is None else y_off[0], y_off[1])
+    a.x_off[0], a.x_off[1], a.y_off[0], a.y_off[1] = xo[0], xo[1], yo[0], yo[1]
+    a.cross = 1 if cross else 0
+    a.x_base = x_base
+    for i, p in enumerate(y_srcs):
+        a.y_src[i] = p
+    a.ws = ws
+    if strips is not None:
+        a.strips[0], a.strips[1] = strips[0].data_ptr(), strips[1].data_ptr()
+        a.ld_strip = strips[0].stride(0)
+    return a
+
+
+class HeadInfo:
+    """What the fused head leaves behind for ClipInfoCELoss / accuracy: `parts` = (sum_i CE(logits_per_image[i]),
+    sum_i CE(logits_per_text[i])) carrying the autograd graph, and the device-side top-1 / top-5 counts."""
+
+    def __init__(self, parts, ws, b, n, layout):
+        self.parts, self.ws, self.b, self.n, self.layout = parts, ws, b, n, layout
+
+    @property
+    def top1_count(self):
+        return self.ws[self.layout.out + 4:self.layout.out + 5]
+
+    @property
+    def top5_count(self):
+        return self.ws[self.layout.out + 5:self.layout.out + 6]
+
+
+class FusedClipHead(torch.autograd.Function):
+    """parts[2], workspace = fused CLIP head on the raw tower outputs (image_features, text_features fp32 [b, E]).
+    Exchange steps when gathering: one bf16 feature all-gather in the forward, one all-gather of 2b+2 floats per rank
+    (row log-sum-exps + upstream gradients) in the backward — instead of the reference's all-reduce of two [N, E]
+    gradients (clip.py:43-49)."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, gather, clamp):
+        lib = ops.lib_for(image_features)
+        img = image_features.float().contiguous()
+        txt = text_features.float().contiguous()
+        b, e = img.shape
+        rank, world = dist_info()
+        gather = bool(gather) and world > 1
+        n, row0 = (world * b, rank * b) if gather else (b, 0)
+        dev = img.device
+        L = HeadLayout.get(lib, b, e)
+        ws = torch.empty(L.total, device=dev, dtype=torch.float32)
+        allb = torch.empty(n, 2 * e, device=dev, dtype=torch.bfloat16)
+        local = allb[row0:row0 + b]
+        ls = logit_scale.detach()
+        if ls.dtype != torch.float32 or not ls.is_cuda:
+            raise RuntimeError("declip_b200: logit_scale must be an fp32 CUDA parameter")
+        feats = (_PTR * 2)(img.data_ptr(), txt.data_ptr())
+        eps = (ctypes.c_float * 2)(0.0, 1e-10)                                         # clip.py:129-130
+        _lib.check(lib.dc_head_prepare(feats, eps, 2, b, e, _PTR(local.data_ptr()), _PTR(ws.data_ptr()), _PTR(ls.data_ptr()),
+                                       100.0 if clamp else float("inf"), _stream()), "dc_head_prepare")
+        if gather:
+            dist.all_gather_into_tensor(allb, local)                                  # in place: `local` is rank's slice
+        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), [allb.data_ptr()], ws.data_ptr())
+        _lib.check(lib.dc_head_forward(ctypes.byref(args), _stream()), "dc_head_forward")
+        ctx.save_for_backward(img, txt, ws, allb)
+        ctx.meta = (b, n, e, row0, gather, world, L)
+        parts = ws[L.out:L.out + 2]
+        ctx.mark_non_differentiable(ws)
+        return parts, ws
+
+    @staticmethod
+    def backward(ctx, gparts, _gws):
+        img, txt, ws, allb = ctx.saved_tensors
+        b, n, e, row0, gather, world, L = ctx.meta
+        lib = ops.lib_for(img)
+        g = gparts.contiguous().float()
+        if gather:
+            ws[L.g:L.g + 2].copy_(g)
+            exch = torch.empty(world, 2 * b + 2, device=img.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(exch.view(-1), ws[L.lse:L.lse + 2 * b + 2])
+        else:
+            exch = ws[L.lse:L.lse + 2 * b + 2]
+        d_img, d_txt = torch.empty_like(img), torch.empty_like(txt)
+        local = allb[row0:row0 + b]
+        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), [allb.data_ptr()], ws.data_ptr())
+        xraw = (_PTR * 2)(img.data_ptr(), txt.data_ptr())
+        eps = (ctypes.c_float * 2)(0.0, 1e-10)
+        dxo = (_PTR * 2)(d_img.data_ptr(), d_txt.data_ptr())
+        _lib.check(lib.dc_head_backward(ctypes.byref(args), _PTR(g.data_ptr()), _PTR(exch.data_ptr()), xraw, eps, dxo,
+                                        _stream()), "dc_head_backward")
+        return d_img, d_txt, ws[L.out + 10:L.out + 11], None, None
+
+
+def fused_clip_head(image_features, text_features, logit_scale, gather, clamp=True):
+    """-> (logits_per_image, logits_per_text) HANDLES: zero-stride [b, N] views that carry `._dc_head` (HeadInfo) for
+    declip_b200.loss_functions.ClipInfoCELoss; they hold no logits (use the compat path when a caller reads them)."""
+    parts, ws = FusedClipHead.apply(image_features, text_features, logit_scale, gather, clamp)
+    b, e = image_features.shape
+    rank, world = dist_info()
+    n = world * b if (gather and world > 1) else b
+    info = HeadInfo(parts, ws, b, n, HeadLayout.get(ops.lib_for(image_features), b, e))
+    li = ws[0:1].expand(b, n)
+    lt = ws[1:2].expand(b, n)
+    li._dc_head = lt._dc_head = info
+    return li, lt

@@ -17,6 +17,12 @@ class ClipInfoCELoss(_Loss):
         rank, _ = F_.dist_info()
         label0 = 0 if l_bs == bs else rank * bs                                    # loss.py:42-45
         labels = label0 + torch.arange(0, bs, dtype=torch.long, device=logits_per_image.device)
+        head = getattr(logits_per_image, "_dc_head", None)
+        if head is not None and getattr(logits_per_text, "_dc_head", None) is head:
+            # fused head (csrc/head.cu): the row cross-entropies were reduced inside the kernel that formed the logits
+            loss = head.parts.sum() / (2.0 * bs)
+            self.stats["top1_count"], self.stats["top5_count"], self.stats["rows"] = head.top1_count, head.top5_count, bs
+            return loss, labels
         loss = F_.ClipInfoCE.apply(logits_per_image, logits_per_text, label0, self.stats)
         return loss, labels
 

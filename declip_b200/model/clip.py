@@ -7,6 +7,7 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from ..runtime import concurrent_towers
 from .modified_resnet import modified_resnet_R50
 from .text_transformer import text_transformers
 from .visual_transformer import visual_transformer_B32
@@ -15,9 +16,13 @@ __all__ = ['clip_vitb32', 'clip_res50', 'CLIP']
 
 
 class CLIP(nn.Module):
-    def __init__(self, image_encode, text_encode, use_allgather):
+    def __init__(self, image_encode, text_encode, use_allgather, fused_head=False):
         super().__init__()
         self.use_allgather = use_allgather
+        # fused_head=True: forward returns two HANDLES instead of logit strips — the strips, ClipInfoCELoss, accuracy and
+        # the whole backward run inside csrc/head.cu and no [b, N] tensor exists; only declip_b200's ClipInfoCELoss
+        # understands them.  False (default): real [b, N] strips for callers that read logits (clip_solver.py:417-422).
+        self.fused_head = fused_head
         self.visual = image_encode
         self.encode_text = text_encode
         self.logit_scale = nn.Parameter(torch.ones([1]))
@@ -59,9 +64,12 @@ class CLIP(nn.Module):
         # The text tower runs first so that autograd (latest node first) runs the IMAGE tower's backward first: its
         # gradient all-reduce — the larger bucket — is then hidden behind the text tower's backward (dist.py).
         # The reference encodes the image first (clip.py:126-127); the two towers are independent, the results identical.
-        text_features = self.encode_text(texts)
-        image_features = self.encode_image(images)
+        with concurrent_towers():        # text tower on a side stream, image tower on the current one (runtime.py)
+            text_features = self.encode_text(texts)
+            image_features = self.encode_image(images)
         gather = (self.training and self.use_allgather) or all_gather             # clip.py:136
+        if self.fused_head and image_features.shape[1] % 256 == 0 and image_features.shape[1] <= 1024:
+            return F_.fused_clip_head(image_features, text_features, self.logit_scale, gather, True)
         logits_per_image, logits_per_text = F_.ClipLogits.apply(image_features, text_features, self.logit_scale,
                                                                 gather, True)
         return logits_per_image, logits_per_text

@@ -6,6 +6,7 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from ..runtime import concurrent_towers
 from .clip import CLIP
 from .modified_resnet import modified_resnet_R50
 from .nn_memory_bank import NNMemoryBankModule
@@ -153,14 +154,15 @@ class DECLIP(CLIP):
             raise NotImplementedError('2-View: Not Implemented')                                    # declip.py:301-302
         images = input['images']
         ids, ids_aug, mlm = self._text_inputs(input)
-        if self.text_mask_type is not None:
-            text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
-                                                                         mask_type=self.text_mask_type)
-            text_features_aug = self.encode_text(ids_aug)
-        else:
-            text_features = self.encode_text(ids)
-            text_features_aug = self.encode_text(ids_aug) if self.EDA else text_features.detach()
-        image_features_1, image_features_2 = self._encode_two_views(images)                         # declip.py:199,225-232
+        with concurrent_towers():        # text passes on a side stream, the two-view image pass on the current one
+            if self.text_mask_type is not None:
+                text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
+                                                                             mask_type=self.text_mask_type)
+                text_features_aug = self.encode_text(ids_aug)
+            else:
+                text_features = self.encode_text(ids)
+                text_features_aug = self.encode_text(ids_aug) if self.EDA else text_features.detach()
+            image_features_1, image_features_2 = self._encode_two_views(images)                     # declip.py:199,225-232
         # SimSiam heads                                                                              declip.py:238-241
         z1 = self.projector(image_features_1)
         z2 = self.projector(image_features_2)

@@ -8,6 +8,7 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from ..runtime import concurrent_towers
 from .declip import DECLIP
 from .filip import weighted_dense_logits
 from .text_transformer import text_transformers
@@ -58,11 +59,12 @@ class DEFILIP(DECLIP):
         images = input['images']
         images_1, images_2 = images[:, :3], images[:, 3:]                                           # defilip.py:275
         ids, ids_aug, mlm = self._text_inputs(input)
-        text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
-                                                                     mask_type=self.text_mask_type)   # :294
-        text_features_aug, word_features_aug = self.encode_text(ids_aug, return_dense=True)          # :295
-        image_features_1, image_d1 = self.encode_image(images_1, return_dense=True)                  # :311-313
-        image_features_2, image_d2 = self.encode_image(images_2, return_dense=True)
+        with concurrent_towers():
+            text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
+                                                                         mask_type=self.text_mask_type)   # :294
+            text_features_aug, word_features_aug = self.encode_text(ids_aug, return_dense=True)      # :295
+            image_features_1, image_d1 = self.encode_image(images_1, return_dense=True)              # :311-313
+            image_features_2, image_d2 = self.encode_image(images_2, return_dense=True)
         z1 = self.projector(image_features_1)                                                        # :316-319
         z2 = self.projector(image_features_2)
         p1 = self.predictor(z1)

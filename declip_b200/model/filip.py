@@ -6,6 +6,7 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from ..runtime import concurrent_towers
 from .clip import CLIP
 from .modified_resnet import modified_resnet_R50
 from .text_transformer import text_transformers
@@ -77,11 +78,12 @@ class FILIP(CLIP):
             text_in = input.get('mlm') if input.get('mlm') is not None else input['token_ids']
         else:
             text_in = self.sample_captions(input['captions'])
-        if self.text_mask_type is not None:
-            text_features, word_features, text_labels = self.encode_text(text_in, mask_type=self.text_mask_type)
-        else:
-            text_features, word_features = self.encode_text(text_in, return_dense=True)
-        image_features_1, image_features_d = self.encode_image(images_1, return_all=True)      # :119
+        with concurrent_towers():
+            if self.text_mask_type is not None:
+                text_features, word_features, text_labels = self.encode_text(text_in, mask_type=self.text_mask_type)
+            else:
+                text_features, word_features = self.encode_text(text_in, return_dense=True)
+            image_features_1, image_features_d = self.encode_image(images_1, return_all=True)  # :119
         li, lt = F_.ClipLogits.apply(image_features_1, text_features, self.logit_scale, True, False)   # :121-129 (no clamp)
         ret = {'logits': (li, lt)}
         if self.return_dense:

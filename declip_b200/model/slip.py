@@ -8,6 +8,7 @@ import torch
 from torch import nn
 
 from .. import functions as F_
+from ..runtime import concurrent_towers
 from .clip import CLIP
 from .declip import _bn
 from .text_transformer import text_transformers
@@ -97,10 +98,11 @@ class SLIP(CLIP):
         images = input['images']
         images_base, images_1, images_2 = images[:, :3], images[:, 3:6], images[:, 6:9]       # slip.py:241
         texts = self._texts(input)
-        text_features = self.encode_text(texts)
-        image_features = self.encode_image(images_base)
-        _, image_sim_1 = self.encode_image(images_1, return_sim=True)
-        _, image_sim_2 = self.encode_image(images_2, return_sim=True)
+        with concurrent_towers():
+            text_features = self.encode_text(texts)
+            image_features = self.encode_image(images_base)
+            _, image_sim_1 = self.encode_image(images_1, return_sim=True)
+            _, image_sim_2 = self.encode_image(images_2, return_sim=True)
         # exp(logit_scale) is NOT clamped here (slip.py:258), as in FILIP
         logits_per_image, logits_per_text = F_.ClipLogits.apply(image_features, text_features, self.logit_scale, True, False)
         image_features = F_.L2Normalize.apply(image_features, 0.0)

@@ -5,6 +5,8 @@ PyTorch's role here is plumbing only — it owns device memory (caching allocato
 stream and autograd bookkeeping.  All arithmetic is in declip_b200/_C.so.
 """
 import ctypes
+import os
+import threading
 
 import torch
 
@@ -73,6 +75,80 @@ def weight_shadow(p, pad_rows=0):
                    "dc_cast_f32_bf16")
         p._dc_shadow_version = p._version
     return sh
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Two-stream tower execution.  The image and the text tower are independent in the forward and in the backward; each
+# is a chain of persistent kernels (one CTA per SM) whose last wave leaves most SMs idle (300 cluster tiles on 74
+# clusters = 4.05 waves for every N = 768 output).  Issued on two streams, the CTAs of one tower's next kernel occupy
+# the SMs the other tower's tail wave leaves free — late-starting CTAs are the high-numbered ones, which own one tile
+# less, so the static tile schedules balance by themselves.
+#   forward : inside `with concurrent_towers():` the FIRST tower runtime that runs goes to the side stream (it forks
+#             before the main stream has any tower work queued); the region's exit joins.
+#   backward: the FIRST tower runtime whose backward node autograd executes goes to the side stream (its incoming
+#             gradient only waits for the head's backward); an end-of-backward callback joins.
+TOWER_STREAMS = os.environ.get("DECLIP_B200_TOWER_STREAMS", "1") != "0"
+_tls = threading.local()
+
+
+def _side_stream(dev):
+    pool = getattr(_tls, "side", None)
+    if pool is None:
+        pool = _tls.side = {}
+    if dev not in pool:
+        pool[dev] = torch.cuda.Stream(device=dev)
+    return pool[dev]
+
+
+class concurrent_towers:
+    """Context manager around the encoder calls of one model forward (see above)."""
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "region", None)
+        _tls.region = self if TOWER_STREAMS else None
+        self.side_rt, self.outputs, self.stream, self.dev = None, [], None, None
+        return self
+
+    def __exit__(self, *exc):
+        _tls.region = self.prev
+        if self.stream is not None:
+            main = torch.cuda.current_stream(self.dev)
+            main.wait_stream(self.stream)
+            for t in self.outputs:              # allocated on the side stream's pool, consumed on the main stream
+                t.record_stream(main)
+        return False
+
+    def stream_for(self, rt, dev):
+        """side stream for the first runtime seen in this region (and its later passes), None (= current) otherwise."""
+        if self.side_rt is None:
+            self.side_rt, self.dev = rt, dev
+            self.stream = _side_stream(dev)
+            self.stream.wait_stream(torch.cuda.current_stream(dev))      # inputs produced on the main stream
+        return self.stream if rt is self.side_rt else None
+
+
+class _BackwardPass:
+    """Per-backward-pass stream assignment (reset by an autograd end-of-backward callback)."""
+
+    def __init__(self):
+        self.side_rt, self.stream, self.dev = None, None, None
+
+    def stream_for(self, rt, dev):
+        if self.side_rt is None:
+            self.side_rt, self.dev = rt, dev
+            self.stream = _side_stream(dev)
+            self.main = torch.cuda.current_stream(dev)     # autograd runs the node on the stream its forward was applied on
+            self.stream.wait_stream(self.main)             # the head's backward produced d(features)
+            torch.autograd.Variable._execution_engine.queue_callback(self.finish)
+        return self.stream if rt is self.side_rt else None
+
+    def finish(self):
+        _tls.bwd = None
+        if self.stream is not None:
+            self.main.wait_stream(self.stream)
+            cur = torch.cuda.current_stream(self.dev)
+            if cur != self.main:
+                cur.wait_stream(self.stream)
 
 
 class TowerRuntime:
@@ -278,6 +354,32 @@ class TowerRuntime:
                     p.grad = v
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _forward_on_stream(rt, inp, params, dense, pre):
+    """rt.forward on the stream the enclosing concurrent_towers() region assigns (the current stream outside one)."""
+    region = getattr(_tls, "region", None)
+    stream = region.stream_for(rt, inp.device) if region is not None and inp.is_cuda else None
+    with (torch.cuda.stream(stream) if stream is not None else _NullCtx()):
+        if stream is not None:
+            inp.record_stream(stream)
+        feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)
+        outs = [feats]
+        if dense:
+            outs.append(words)
+        if pre:
+            outs.append(rt.pre_features(cfg, ws).float())
+    if stream is not None:
+        region.outputs.extend(outs)
+    return outs, (inp_used, cfg, ws)
+
+
 class _TowerFunction(torch.autograd.Function):
     """features [, words] = tower(inp; params).  One C-ABI call forward, one backward.  Parameter gradients are
     written into p.grad by the runtime (see TowerRuntime.backward); autograd only carries d(features), d(words)."""
@@ -285,14 +387,9 @@ class _TowerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rt, inp, anchor, dense, pre=False):
         params = rt._params()
-        feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)
+        outs, (inp_used, cfg, ws) = _forward_on_stream(rt, inp, params, dense, pre)
         rt._outstanding += 1
         ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense, ctx.pre = rt, cfg, inp_used, ws, params, dense, pre
-        outs = [feats]
-        if dense:
-            outs.append(words)
-        if pre:
-            outs.append(rt.pre_features(cfg, ws).float())
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
@@ -301,11 +398,23 @@ class _TowerFunction(torch.autograd.Function):
         rest = list(rest)
         dwords = rest.pop(0) if ctx.dense else None
         dpre = rest.pop(0) if ctx.pre else None
-        rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords, dpre)
-        ctx.ws = None
-        rt._outstanding = max(0, rt._outstanding - 1)
-        if rt._outstanding == 0 and rt.grad_ready_hook is not None:
-            rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
+        stream = None
+        if TOWER_STREAMS:
+            bp = getattr(_tls, "bwd", None)
+            if bp is None:
+                bp = _tls.bwd = _BackwardPass()
+            stream = bp.stream_for(rt, ctx.ws.device)
+        with (torch.cuda.stream(stream) if stream is not None else _NullCtx()):
+            if stream is not None:
+                ctx.ws.record_stream(stream)            # allocated on another stream's pool in the forward
+                for t in (dfeats, dwords, dpre, ctx.inp):
+                    if t is not None:
+                        t.record_stream(stream)
+            rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords, dpre)
+            ctx.ws = None
+            rt._outstanding = max(0, rt._outstanding - 1)
+            if rt._outstanding == 0 and rt.grad_ready_hook is not None:
+                rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
         return None, None, None, None, None
 
 
@@ -318,10 +427,5 @@ def run_tower(rt, inp, dense=False, pre=False):
         anchor = next((p for p in params.values() if p.requires_grad), None)
         if anchor is not None:
             return _TowerFunction.apply(rt, inp, anchor, dense, pre)
-    out = rt.forward(inp, params, dense)
-    outs = [out[0]]
-    if dense:
-        outs.append(out[4])
-    if pre:
-        outs.append(rt.pre_features(out[2], out[3]).float())
+    outs, _ = _forward_on_stream(rt, inp, params, dense, pre)
     return outs[0] if len(outs) == 1 else tuple(outs)

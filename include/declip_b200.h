@@ -241,6 +241,52 @@ int dc_add_bf16(const void* a, const void* b, void* out, size_t n, dc_stream_t s
 int dc_attnpool_assemble(const void* x, const float* pos, void* tokens, int batch, int P, int C, dc_stream_t stream);
 int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, int C, dc_stream_t stream);
 
+/* ------------------------------------------------------------------ fused distributed contrastive head (head.cu)
+ * Replaces, for a symmetric image/text pair, the whole chain clip.py:129-146 (normalise, AllGather, two logit
+ * strips) + loss_functions/loss.py:40-50 (ClipInfoCELoss) + utils/misc.py:415-428 (accuracy) and its autograd backward
+ * (clip.py:43-49 all_reduce of the gathered-tensor gradients) by three launches; no [b, N] strip reaches HBM.
+ *   dc_head_prepare : y_f = x_f / (||x_f|| + eps_f) as bf16 into out_rows[b, n_feats * e] (feature f at columns
+ *                     [f e, (f+1) e)) — this rank's slice of the gather buffer — and clears the workspace accumulators.
+ *   dc_head_forward : per direction d: logits[i, j] = s <X_d[i], Y_d[j]>, i local, j over all n gathered rows; writes
+ *                     ws[out..]: sum_i CE_d (2 floats), sum_i (E_softmax[logit] - label logit) (2 floats; times
+ *                     exp(logit_scale)/s it is d sum CE / d logit_scale), top-1 / top-5 counts of direction 0, and the
+ *                     row log-sum-exps ws[lse..] = [2][b].  strips[d] != NULL additionally stores the fp32 strip
+ *                     (compat mode for callers that consume logits).
+ *   dc_head_backward: exch = [n_ranks][2 b + 2] — every rank's {lse[0][b], lse[1][b], g[0], g[1]} with g[d] the upstream
+ *                     gradient of sum CE_d (an all-gather of ws[lse .. g+2)); writes dx_out[d] = d loss / d raw X_d
+ *                     feature (through the normalisation), including — when `cross` — the terms the reference receives
+ *                     through AllGather.backward from the other ranks' strips.
+ * y_src: n_src == 1 -> one buffer holding all n rows (NCCL all-gather result); n_src == world -> y_src[r] = rank r's
+ * b rows (peer-mapped symmetric memory; the kernel reads them over NVLink, no collective).  e in {256,512,768,1024}. */
+typedef struct {
+  int b, n, e;              /* local rows, gathered rows, feature dim */
+  int ld;                   /* row stride of the feature buffers in elements (n_feats * e) */
+  int n_src;
+  int row0;                 /* global row index of local row 0 (rank * b): labels are row0 + i (loss.py:45) */
+  int x_off[2], y_off[2];   /* column offset of the X / Y feature of each direction inside a row */
+  int cross;                /* 1: the two directions are transposes of each other (ClipInfoCELoss(li, lt)) */
+  int ld_strip;
+  const void* x_base;       /* bf16 [b, ld]: this rank's rows */
+  const void* y_src[8];
+  float* ws;                /* dc_head_workspace_floats(b, e) floats; carries the scale computed by dc_head_prepare */
+  float* strips[2];
+} dc_head_args;
+size_t dc_head_workspace_floats(int b, int e);
+/* offsets (floats) into the workspace: {out[16], lse[2][b], g[2], alab[2][b], ea[2][b], counters, dxn[2][b][e], total};
+ * out: 0,1 sum CE_d; 2,3 sum (E_softmax[logit] - label logit)_d; 4 / 5 top-1 / top-5 counts of direction 0; 8 s; 9 exp(ls);
+ * 10 d loss / d logit_scale. */
+int dc_head_layout(int b, int e, long long* offsets8);
+/* logit_scale: the raw parameter on the device — s = min(exp(logit_scale), scale_max) in the forward, d s / d logit_scale
+ * = exp(logit_scale) (the reference clamps `.data`, clip.py:133-134) — or NULL for the constant scale `scale_max`.
+ * ws[out + 8] = s, ws[out + 9] = exp(logit_scale); dc_head_backward leaves d loss / d logit_scale in ws[out + 10]. */
+int dc_head_prepare(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows, float* ws,
+                    const float* logit_scale, float scale_max, dc_stream_t stream);
+int dc_head_forward(const dc_head_args* a, dc_stream_t stream);
+/* g_own[2] (device): upstream gradients of this rank's sum CE_d; exch as described above (its own rank's g slots are
+ * not read: g_own is used instead, so a single-rank step needs no copy at all). */
+int dc_head_backward(const dc_head_args* a, const float* g_own, const float* exch, const float* const* x_raw,
+                     const float* eps2, float* const* dx_out, dc_stream_t stream);
+
 /* ------------------------------------------------------------------ host-side text front end (no device work)
  * Byte-pair-encoding tokenizer = prototype/model/utils/text_utils/simple_tokenizer.py:66-134 (OpenAI CLIP BPE plus the
  * extra <|mask|> token: vocabulary = merges + 515) and the truncation / zero padding of TextTransformer.tokenize
