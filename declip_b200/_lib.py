@@ -68,6 +68,9 @@ SIGNATURES = {
     "dc_last_error": (ctypes.c_char_p, []),
     "dc_init": (c_int, [c_int]),
     "dc_sm_count": (c_int, []),
+    "dc_set_sm_reserve": (c_int, [c_int]),
+    "dc_cast_bf16_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_int, c_void_p]),
+    "dc_set_backward_progress_cb": (c_int, [c_void_p, c_void_p, c_int]),
     "dc_launch_count": (c_ll, []),
     "dc_gemm_bf16": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
     "dc_set_gemm_2cta": (c_int, [c_int]),

@@ -51,6 +51,9 @@ struct Carver {
 
 constexpr int MAX_LAYERS = 48;
 
+struct ProgressHook { dc_progress_cb cb; void* user; int every; };
+static thread_local ProgressHook g_progress = {nullptr, nullptr, 1};
+
 struct LayerWs {
   bf16 *ln1, *qkv, *attn, *xmid, *ln2, *u, *h;
   float *mean1, *rstd1, *mean2, *rstd2, *lse;
@@ -247,6 +250,8 @@ static int layers_backward(const dc_tower_cfg& c, TowerWs& w, const void* const*
     DC_TRY(linear_wgrad(w.dqkv, L.ln1, M, 3 * D, D, g[0], nullptr, st));
     float* dcol_prev = (l > 0) ? grads[12 * (l - 1) + 9] : nullptr;                     // c_proj.bias of layer l-1
     DC_TRY(dc_layernorm_bwd(w.dtmp, w.xs[l], f[0], L.mean1, L.rstd1, dmid, dx, g[4], g[5], dcol_prev, M, D, st));
+    // gradients of layers >= l are final in stream order (c_proj.bias of layer l-1 belongs to the NEXT slice)
+    if (g_progress.cb != nullptr && l > 0 && l % g_progress.every == 0) g_progress.cb(g_progress.user, l);
   }
   return 0;
 }
@@ -256,6 +261,13 @@ static int layers_backward(const dc_tower_cfg& c, TowerWs& w, const void* const*
 using namespace dc;
 
 extern "C" {
+
+int dc_set_backward_progress_cb(dc_progress_cb cb, void* user, int every) {
+  g_progress.cb = cb;
+  g_progress.user = user;
+  g_progress.every = every < 1 ? 1 : every;
+  return 0;
+}
 
 size_t dc_tower_workspace_bytes(const dc_tower_cfg* cfg) {
   if (check_cfg(cfg) != 0) return 0;

@@ -11,7 +11,8 @@ namespace dc {
 int set_error(const char* msg);
 int set_error_cuda(const char* what, cudaError_t e);
 void count_launch();
-int sm_count();
+int sm_count();            // SMs the persistent kernels may fill: device SMs minus dc_set_sm_reserve()
+int set_sm_reserve(int n);
 
 // 2-D bf16 tensor map, 128-byte swizzle.  `inner` = contiguous extent (elements), `outer` = rows,
 // `ld` = row stride (elements); box = {box_inner (must be 64 -> 128 B), box_outer <= 256}.

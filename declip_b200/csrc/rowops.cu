@@ -241,6 +241,31 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
   }
 }
 
+__global__ void __launch_bounds__(256) uncast_kernel(const bf16* __restrict__ src, float* __restrict__ dst, size_t n,
+                                                     float scale, bool accumulate) {
+  const size_t nv = n >> 3;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src) + i), v);
+    float4* d = reinterpret_cast<float4*>(dst) + 2 * i;
+    float4 a = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+    float4 b = make_float4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale);
+    if (accumulate) {
+      const float4 pa = d[0], pb = d[1];
+      a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+      b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+    }
+    d[0] = a;
+    d[1] = b;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nv << 3) + threadIdx.x;
+    const float v = __bfloat162float(src[i]) * scale;
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
 __global__ void __launch_bounds__(256) multi_cast_kernel(const dc_cast_entry* __restrict__ table) {
   const dc_cast_entry e = table[blockIdx.y];
   const float* src = e.src;
@@ -635,6 +660,15 @@ int dc_cast_f32_bf16(const float* src, void* dst, size_t n, dc_stream_t stream) 
   if (n == 0) return 0;
   cast_kernel<<<grid_for(n / 8 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<bf16*>(dst), n);
   DC_CHECK_LAUNCH("cast");
+  return 0;
+}
+
+int dc_cast_bf16_f32(const void* src, float* dst, size_t n, float scale, int accumulate, dc_stream_t stream) {
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) return set_error("cast_bf16_f32: 16-byte aligned buffers");
+  uncast_kernel<<<grid_for(n / 8 + 1, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(src), dst, n, scale,
+                                                                                        accumulate != 0);
+  DC_CHECK_LAUNCH("uncast");
   return 0;
 }
 

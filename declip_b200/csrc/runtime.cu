@@ -29,7 +29,12 @@ int set_error_cuda(const char* what, cudaError_t e) {
   return static_cast<int>(e) ? static_cast<int>(e) : -1;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+static std::atomic<int> g_sm_reserve{0};
+int sm_count() {
+  const int n = (g_sm_count > 0 ? g_sm_count : 148) - g_sm_reserve.load(std::memory_order_relaxed);
+  return n < 2 ? 2 : n;
+}
+int set_sm_reserve(int n) { return g_sm_reserve.exchange(n < 0 ? 0 : n); }
 
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, long long inner, long long outer, long long ld, int box_inner,
                  int box_outer, int swizzle_bytes) {
@@ -103,6 +108,8 @@ const char* dc_last_error(void) { return dc::g_err; }
 long long dc_launch_count(void) { return dc::g_launches.load(); }
 
 int dc_sm_count(void) { return dc::sm_count(); }
+
+int dc_set_sm_reserve(int n) { return dc::set_sm_reserve(n); }
 
 int dc_init(int device) {
   static std::mutex mu;

@@ -170,6 +170,7 @@ class TowerRuntime:
         self.grad_flat = None
         self._outstanding = 0     # forwards (under autograd) whose backward has not run yet
         self.grad_ready_hook = None   # called (rt) when every outstanding backward of this tower has been enqueued
+        self.progress_hook = None     # (ctypes callback, every): dc_set_backward_progress_cb during the LAST outstanding backward
 
     # ------------------------------------------------------------------ parameter plumbing
     def _params(self):
@@ -214,6 +215,7 @@ class TowerRuntime:
             gtotal += (params[n].numel() + 63) // 64 * 64
         self.grad_flat = torch.zeros(gtotal, device=dev, dtype=torch.float32)
         self.grad_offs = goffs
+        self.layer_grad_end = goffs[12 * self.layers]       # the per-layer gradients come first, then the tower's own
         self.grad_ptrs = _ptr_array([self.grad_flat.data_ptr() + 4 * o for o in goffs])
         self._key = key
         self._versions = None
@@ -325,6 +327,18 @@ class TowerRuntime:
         dfeats = dfeats.float().contiguous()
         if dwords is not None:
             dwords = dwords.to(torch.bfloat16).contiguous()
+        self.writing_flat = tmp is None         # this pass accumulates straight into grad_flat (the slices are / become p.grad)
+        hook = self.progress_hook if (self.progress_hook is not None and self._outstanding == 1 and not foreign) else None
+        if hook is not None:     # layer-group progress reports -> gradient buckets go on the wire during the backward
+            self.lib.dc_set_backward_progress_cb(ctypes.cast(hook[0], _PTR), None, hook[1])
+        try:
+            self._run_backward(cfg, inp, dfeats, dense, dwords, dpre, ptrs, ws)
+        finally:
+            if hook is not None:
+                self.lib.dc_set_backward_progress_cb(None, None, 1)
+        self._finish_backward(params, views, tmp)
+
+    def _run_backward(self, cfg, inp, dfeats, dense, dwords, dpre, ptrs, ws):
         if self.kind == "vit":
             if dpre is not None:
                 dpre = dpre.to(torch.bfloat16).contiguous()
@@ -337,6 +351,8 @@ class TowerRuntime:
                                                  int(dense), _PTR(dwords.data_ptr()) if dwords is not None else None,
                                                  self.w_bf16, self.w_f32, ptrs, _PTR(ws.data_ptr()), _stream()),
                        "dc_text_backward")
+
+    def _finish_backward(self, params, views, tmp):
         if tmp is not None:
             for n, o in zip(self.grad_names, self.grad_offs):
                 p = params[n]

@@ -35,6 +35,10 @@ const char* dc_last_error(void);
  * dynamic shared-memory limits of every kernel.  Must be called once per process/device. */
 int dc_init(int device);
 int dc_sm_count(void);
+/* Persistent kernels (GEMM, attention, LayerNorm backward) size their grids to dc_sm_count() = device SMs - reserve.  A
+ * data-parallel caller reserves the SMs its collective kernels occupy (NCCL: one CTA per channel) while gradient buckets
+ * are in flight, so that a collective CTA never waits behind a whole persistent tile loop.  Returns the previous value. */
+int dc_set_sm_reserve(int n);
 
 /* ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
  * out[M,N] (op)= epilogue(alpha * sum_k A(m,k) * B(n,k))
@@ -97,6 +101,8 @@ int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
 int dc_colsum_bf16(const void* x, int ldx, float* out, int rows, int cols, dc_stream_t stream);
 /* fp32 -> bf16 cast of n elements (weight shadows). */
 int dc_cast_f32_bf16(const float* src, void* dst, size_t n, dc_stream_t stream);
+/* dst[i] (+)= src[i] * scale, bf16 -> fp32 (gradient buckets travel as bf16 and return to the fp32 .grad buffer) */
+int dc_cast_bf16_f32(const void* src, float* dst, size_t n, float scale, int accumulate, dc_stream_t stream);
 /* table-driven multi-tensor cast: table (device) holds n_tensors entries {src, dst, numel}. */
 typedef struct { const float* src; void* dst; unsigned long long numel; } dc_cast_entry;
 int dc_multi_cast_f32_bf16(const dc_cast_entry* table_dev, int n_tensors, unsigned long long max_numel,
@@ -324,6 +330,14 @@ typedef struct {
 size_t dc_tower_workspace_bytes(const dc_tower_cfg* cfg);
 /* dense_out (bf16 [batch*(L-1), width], may be NULL): the patch tokens of the last block, `x[:, 1:, :]` that
  * VisualTransformer.forward returns with return_dense (visual_transformer.py:68); ddense is its gradient (or NULL). */
+/* Host-side progress hook of the tower BACKWARD executors: `cb(user, l)` is called from the launching thread right
+ * after the kernels of transformer layer l have been enqueued (l counts down from layers-1 to 0), whenever
+ * l % every == 0.  Every gradient of layers >= l is then complete in stream order, so a data-parallel caller can record
+ * an event and start reducing that slice while the earlier layers still run (utils/dist.py:63-74 overlaps per parameter
+ * through autograd hooks).  Per calling thread; cb = NULL clears it. */
+typedef void (*dc_progress_cb)(void* user, int layer);
+int dc_set_backward_progress_cb(dc_progress_cb cb, void* user, int every);
+
 int dc_vit_forward(const dc_tower_cfg* cfg, const float* images, long long sample_stride,
                    const void* const* w_bf16, const float* const* w_f32, void* workspace, float* features,
                    void* dense_out, dc_stream_t stream);
