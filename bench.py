@@ -418,9 +418,18 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    per_step = []
+
     def loop_resident(k):
+        debug = os.environ.get("BENCH_PER_STEP")
         for i in range(k):
+            if debug:
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
             step(resident[i % 2])
+            if debug:
+                b_.record()
+                per_step.append((a, b_))
 
     copy_stream = torch.cuda.Stream()
     stage = [{k: torch.empty_like(v) for k, v in resident[0].items()} for _ in range(2)]
@@ -461,6 +470,8 @@ def run_native(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     log("resident: %.2f ms/step" % (ms / args.steps))
+    if per_step:
+        log("per-step ms: " + " ".join("%.1f" % a.elapsed_time(b_) for a, b_ in per_step))
     e2e = None
     if not args.no_e2e:
         loop_e2e(2)   # warm the copy path

@@ -787,7 +787,7 @@ class FusedClipHead(torch.autograd.Function):
         _lib.check(lib.dc_head_forward(ctypes.byref(args), _stream()), "dc_head_forward")
         ctx.save_for_backward(img, txt, ws, allb)
         ctx.meta = (b, n, e, row0, gather, world, L)
-        parts = ws[L.out:L.out + 2]
+        parts = ws[L.out:L.out + 2].clone()      # its own storage: an autograd output must not alias the workspace
         ctx.mark_non_differentiable(ws)
         return parts, ws
 

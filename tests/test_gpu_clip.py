@@ -1,8 +1,10 @@
 """GPU parity proper: the CUDA dual-encoder path (through the C ABI) against
   (1) the oracle restatement on the same seeded inputs, and
   (2) the golden vectors generated from the reference's own modules (tests/golden/).
-Stated tolerance (bf16 storage / fp32 accumulate vs the reference's fp32): |d loss| <= 2e-2,
-feature cosine >= 0.999, per-parameter gradient cosine >= 0.98 (>= 0.99 for the large matrices)."""
+Stated tolerance (bf16 storage / fp32 accumulate vs the reference's fp32; ~3x the worst value measured on B200,
+profiles/r02_parity_report_*.json): |d loss| <= 2e-3, feature / logits cosine >= 0.9995, per-parameter gradient cosine
+>= 0.995 (>= 0.998 for the weight matrices), gradient-norm ratio within 3 %.  The b = 512 / full-depth cases and the
+DeCLIP / FILIP goldens are in tests/test_gpu_fullsize.py (same table, tests/parity_cases.py)."""
 import pytest
 import torch
 
@@ -53,12 +55,12 @@ def test_step_matches_reference_golden(cuda_dev, name):
         ft = model.encode_text(ids)
     rows_i = torch.nn.functional.cosine_similarity(fi.cpu(), g["image_features"], dim=1)
     rows_t = torch.nn.functional.cosine_similarity(ft.cpu(), g["text_features"], dim=1)
-    assert rows_i.min().item() > 0.999, rows_i
-    assert rows_t.min().item() > 0.999, rows_t
+    assert rows_i.min().item() > 0.9995, rows_i
+    assert rows_t.min().item() > 0.9995, rows_t
     li, lt, loss, labels = _step(model, images, ids)
-    assert abs(loss.item() - g["loss"]) <= 2e-2, (loss.item(), g["loss"])
+    assert abs(loss.item() - g["loss"]) <= 2e-3, (loss.item(), g["loss"])
     assert torch.equal(labels.cpu(), g["labels"])
-    assert _cos(li.cpu(), g["logits_per_image"]) > 0.999
+    assert _cos(li.cpu(), g["logits_per_image"]) > 0.9995
     params = dict(model.named_parameters())
     assert params["visual.conv1.weight"].grad is None                     # frozen (visual_transformer.py:12)
     assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
@@ -71,10 +73,10 @@ def test_step_matches_reference_golden(cuda_dev, name):
         worst.append((cs, nr, k))
     worst.sort()
     msg = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:8])
-    assert worst[0][0] > 0.98, msg
+    assert worst[0][0] > 0.995, msg
     big = [w for w in worst if "weight" in w[2] and "ln_" not in w[2]]
-    assert min(w[0] for w in big) > 0.99, msg
-    assert all(0.9 < w[1] < 1.1 for w in worst), msg
+    assert min(w[0] for w in big) > 0.998, msg
+    assert all(0.97 < w[1] < 1.03 for w in worst), msg
 
 
 def test_step_matches_oracle_restatement(cuda_dev):
@@ -84,10 +86,10 @@ def test_step_matches_oracle_restatement(cuda_dev):
     model, sd, images, ids = _build(case, cuda_dev)
     out = clip_ref.clip_step(sd, images.cpu(), ids.cpu())
     li, lt, loss, labels = _step(model, images, ids)
-    assert abs(loss.item() - out["loss"].item()) <= 1e-2
+    assert abs(loss.item() - out["loss"].item()) <= 2e-3
     params = dict(model.named_parameters())
     for k, gref in out["grads"].items():
-        assert _cos(params[k].grad.cpu(), gref) > 0.99, k
+        assert _cos(params[k].grad.cpu(), gref) > 0.995, k
 
 
 def test_grad_accumulation_and_zero_grad_modes(cuda_dev):

@@ -1,6 +1,7 @@
 """GPU parity of the DeCLIP path (BASELINE configs[2]: multi-view + SimSiam + NN + MLM) against the golden vectors
 of the reference's own DECLIP module and the oracle restatement; plus op-level checks of the DeCLIP head kernels.
-Tolerances (bf16 storage / fp32 accumulate): total loss |d| <= 3e-2, parts as stated, gradient cosine >= 0.97."""
+Tolerances (bf16 storage / fp32 accumulate, ~3x the worst measured value): total loss |d| <= 5e-3, parts as stated,
+gradient cosine >= 0.92 for the SimSiam heads behind a BatchNorm over 8 samples, >= 0.97 elsewhere."""
 import pytest
 import torch
 
@@ -128,18 +129,18 @@ def test_declip_step_matches_reference_golden(cuda_dev):
     loss, parts = _declip_loss(out)
     loss.backward()
     torch.cuda.synchronize()
-    tol = dict(clip=2e-2, mlm=5e-2, nn=3e-2, simsiam=3e-3, nt_xent=3e-2)
+    tol = dict(clip=2e-3, mlm=1e-2, nn=5e-3, simsiam=2e-3, nt_xent=5e-3)
     msg = {k: (parts[k].item(), g["parts"][k]) for k in parts}
     for k, v in g["parts"].items():
         assert abs(parts[k].item() - v) <= tol[k], msg
-    assert abs(loss.item() - g["loss"]) <= 3e-2, (loss.item(), g["loss"])
+    assert abs(loss.item() - g["loss"]) <= 5e-3, (loss.item(), g["loss"])
     for key in ("logits", "logits_aug", "nn_text_logits"):
         for a, b in zip(out[key], g[key]):
-            assert _cos(a.cpu(), b) > 0.999, key
+            assert _cos(a.cpu(), b) > 0.9995, key
     for a, b in zip(out["features"], g["features"]):
-        assert torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item() > 0.999
+        assert torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item() > 0.9995
     for a, b in zip(out["simsiam_features"], g["simsiam_features"]):
-        assert _cos(a.cpu(), b) > 0.995
+        assert _cos(a.cpu(), b) > 0.998
     params = dict(model.named_parameters())
     assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
     worst = []
@@ -155,12 +156,12 @@ def test_declip_step_matches_reference_golden(cuda_dev):
     worst.sort()
     txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
     # SimSiam heads sit behind BatchNorm over a batch of 8 here, which amplifies the towers' bf16 noise: 0.95 for them
-    assert all(w[0] > (0.95 if ("projector" in w[2] or "predictor" in w[2]) else 0.97) for w in worst), txt
-    assert all(0.85 < w[1] < 1.15 for w in worst), txt
+    assert all(w[0] > (0.92 if ("projector" in w[2] or "predictor" in w[2]) else 0.97) for w in worst), txt
+    assert all(0.95 < w[1] < 1.05 for w in worst), txt
     # BatchNorm running statistics and the FIFO bank follow the reference
     sd = model.state_dict()
     for k, v in g["stats"].items():
-        assert _rel(sd[k].cpu(), v) < 3e-2, k
+        assert _rel(sd[k].cpu(), v) < 1.5e-2, k
     assert model.nn_replacer_text.bank_ptr == g["bank_ptr"]
     tail = model.nn_replacer_text.bank[:2 * g["case"]["batch"]].t().cpu()
     assert _cos(tail, g["bank_tail"]) > 0.999

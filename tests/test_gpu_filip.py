@@ -1,6 +1,6 @@
 """GPU parity of the FILIP path (BASELINE configs[4]: token-wise late interaction) against the golden vectors of the
-reference's own FILIP module.  Tolerance: losses |d| <= 3e-2, logits cosine >= 0.995 (the top-16 token selection is
-discrete: a near-tie resolved differently under bf16 moves a logit slightly), gradient cosine >= 0.95."""
+reference's own FILIP module.  Tolerance (~3x the worst measured value): losses |d| <= 3e-3 / 5e-3, logits cosine >= 0.9995 (the top-16 token
+selection is discrete: a near-tie resolved differently under bf16 moves a logit slightly), gradient cosine >= 0.96."""
 import pytest
 import torch
 
@@ -60,12 +60,12 @@ def test_filip_step_matches_reference_golden(cuda_dev):
     loss = clip_loss * W["clip_loss"] + dense_loss * W["clip_dense_loss"]
     loss.backward()
     torch.cuda.synchronize()
-    assert abs(clip_loss.item() - g["parts"]["clip"]) <= 2e-2
-    assert abs(dense_loss.item() - g["parts"]["dense"]) <= 3e-2, (dense_loss.item(), g["parts"]["dense"])
+    assert abs(clip_loss.item() - g["parts"]["clip"]) <= 3e-3
+    assert abs(dense_loss.item() - g["parts"]["dense"]) <= 5e-3, (dense_loss.item(), g["parts"]["dense"])
     for a, b in zip(out["logits"], g["logits"]):
-        assert _cos(a.cpu(), b) > 0.999
+        assert _cos(a.cpu(), b) > 0.9995
     for a, b in zip(out["dense_logits"], g["dense_logits"]):
-        assert _cos(a.cpu(), b) > 0.995
+        assert _cos(a.cpu(), b) > 0.9995
     params = dict(model.named_parameters())
     assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
     worst = []
@@ -74,5 +74,5 @@ def test_filip_step_matches_reference_golden(cuda_dev):
         worst.append((_cos(mine[golden.sample_index(mine.numel())], ref["sample"]), mine.norm().item() / (ref["norm"] + 1e-20), k))
     worst.sort()
     txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
-    assert worst[0][0] > 0.95, txt
-    assert all(0.85 < w[1] < 1.15 for w in worst), txt
+    assert worst[0][0] > 0.96, txt
+    assert all(0.9 < w[1] < 1.1 for w in worst), txt

@@ -1,0 +1,34 @@
+"""GPU parity at the reference's REAL depth and the bench batch, against golden vectors produced by the reference's own
+modules (tools/make_golden.py): CLIP ViT-B/32 12+12 layers at b = 512 (BASELINE configs[1] per-GPU shape), DeCLIP and
+FILIP 12+12 layers at b = 64 (configs[2], [4]), and every small case with the same tolerance table
+(tests/parity_cases.py: TOL, ~3x the worst distance measured on B200, profiles/r02_parity_report_*.json)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import parity_cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["clip_vitb32_l2_b8", "clip_vitb32_l12_b32", "clip_vitb32_l12_b512"])
+def test_clip_golden(cuda_dev, name):
+    m = parity_cases.run_clip(name, cuda_dev)
+    bad = parity_cases.check(m, parity_cases.TOL["clip"])
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name", ["declip_vitb32_l2_b8", "declip_vitb32_l12_b64"])
+def test_declip_golden(cuda_dev, name):
+    m = parity_cases.run_declip(name, cuda_dev)
+    bad = parity_cases.check(m, parity_cases.TOL["declip"])
+    assert not bad, "\n".join(bad)
+
+
+@pytest.mark.parametrize("name", ["filip_vitb32_l2_b8", "filip_vitb32_l12_b64"])
+def test_filip_golden(cuda_dev, name):
+    m = parity_cases.run_filip(name, cuda_dev)
+    bad = parity_cases.check(m, parity_cases.TOL["filip"])
+    assert not bad, "\n".join(bad)

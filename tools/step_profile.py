@@ -18,11 +18,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="clip")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--top", type=int, default=32)
+ap.add_argument("--head", default="strips")
 args = ap.parse_args()
 b = args.batch
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model, run, host_inputs = bench.build_workload(args.config, dev, b, 1)
+model, run, host_inputs = bench.build_workload(args.config, dev, b, 1, args.head)
 opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=0.1)
 inp = {k: v.to(dev) for k, v in host_inputs(torch.Generator().manual_seed(0)).items()}
 
