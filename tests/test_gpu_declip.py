@@ -121,52 +121,6 @@ def _declip_loss(out, world=1):
     return loss, dict(clip=clip, mlm=mlm, nn=nn_, simsiam=sim, nt_xent=nt)
 
 
-def test_declip_step_matches_reference_golden(cuda_dev):
-    from oracle import golden
-    g = golden.load("declip_vitb32_l2_b8")
-    model, batch = _build(g["case"], cuda_dev)
-    out = model(batch, return_dict=True)
-    loss, parts = _declip_loss(out)
-    loss.backward()
-    torch.cuda.synchronize()
-    tol = dict(clip=2e-3, mlm=1e-2, nn=5e-3, simsiam=2e-3, nt_xent=5e-3)
-    msg = {k: (parts[k].item(), g["parts"][k]) for k in parts}
-    for k, v in g["parts"].items():
-        assert abs(parts[k].item() - v) <= tol[k], msg
-    assert abs(loss.item() - g["loss"]) <= 5e-3, (loss.item(), g["loss"])
-    for key in ("logits", "logits_aug", "nn_text_logits"):
-        for a, b in zip(out[key], g[key]):
-            assert _cos(a.cpu(), b) > 0.9995, key
-    for a, b in zip(out["features"], g["features"]):
-        assert torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item() > 0.9995
-    for a, b in zip(out["simsiam_features"], g["simsiam_features"]):
-        assert _cos(a.cpu(), b) > 0.998
-    params = dict(model.named_parameters())
-    assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
-    worst = []
-    for k, ref in g["grads"].items():
-        mine = params[k].grad.detach().float().reshape(-1).cpu()
-        if ref["norm"] < 1e-6:
-            # biases feeding a BatchNorm (linear*.bias, bn3.bias -> predictor.linear1 -> bn1): the exact gradient is
-            # zero, the reference holds fp32 round-off (~1e-10); require ours to be numerically zero as well
-            assert mine.abs().max().item() < 1e-4, k
-            continue
-        cs = _cos(mine[golden.sample_index(mine.numel())], ref["sample"])
-        worst.append((cs, mine.norm().item() / (ref["norm"] + 1e-20), k))
-    worst.sort()
-    txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
-    # SimSiam heads sit behind BatchNorm over a batch of 8 here, which amplifies the towers' bf16 noise: 0.95 for them
-    assert all(w[0] > (0.92 if ("projector" in w[2] or "predictor" in w[2]) else 0.97) for w in worst), txt
-    assert all(0.95 < w[1] < 1.05 for w in worst), txt
-    # BatchNorm running statistics and the FIFO bank follow the reference
-    sd = model.state_dict()
-    for k, v in g["stats"].items():
-        assert _rel(sd[k].cpu(), v) < 1.5e-2, k
-    assert model.nn_replacer_text.bank_ptr == g["bank_ptr"]
-    tail = model.nn_replacer_text.bank[:2 * g["case"]["batch"]].t().cpu()
-    assert _cos(tail, g["bank_tail"]) > 0.999
-
-
 def test_nt_xent_family(cuda_dev, monkeypatch):
     """NT_Xent / NT_Xent_gather / NTXentLoss (a18) against the reference-pinned restatements."""
     from declip_b200 import functions as F_

@@ -33,46 +33,3 @@ def test_groupmax_and_scores_ops(cuda_dev):
     assert _cos(out, ref) > 0.9995
     assert _cos(g_d, d1.grad) > 0.98 and _cos(g_s, sel.grad) > 0.98
     assert abs(g_l.item() - ls.grad.item()) < 0.05 * abs(ls.grad.item()) + 1e-2
-
-
-def test_filip_step_matches_reference_golden(cuda_dev):
-    from declip_b200.loss_functions import ClipInfoCELoss
-    from declip_b200.model import model_entry
-    from oracle import golden
-    from oracle.filip_ref import LOSS_WEIGHTS as W
-    g = golden.load("filip_vitb32_l2_b8")
-    c = g["case"]
-    cfg = dict(type='filip_vitb32', kwargs=dict(
-        image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]),
-        text_encode=dict(bpe_path=None, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
-                         embed_dim=c["embed_dim"], transformer_layers=c["t_layers"]),
-        clip=dict(use_allgather=True, text_mask_type='MLM', return_dense=True, select_topk=True, feature_dim=c["embed_dim"],
-                  mask_rate=0.5, patch_number=14)))
-    model = model_entry(cfg)
-    sd, images, mlm_ids, mlm_labels = golden.filip_inputs(c)
-    model.load_state_dict(sd, strict=True)
-    model = model.to(cuda_dev).train()
-    out = model({"images": images.to(cuda_dev), "token_ids": mlm_ids.to(cuda_dev),
-                 "mlm": (mlm_ids.to(cuda_dev), mlm_labels)}, return_dict=True)
-    crit = ClipInfoCELoss()
-    clip_loss = crit(*out["logits"])[0]
-    dense_loss = crit(*out["dense_logits"])[0]
-    loss = clip_loss * W["clip_loss"] + dense_loss * W["clip_dense_loss"]
-    loss.backward()
-    torch.cuda.synchronize()
-    assert abs(clip_loss.item() - g["parts"]["clip"]) <= 3e-3
-    assert abs(dense_loss.item() - g["parts"]["dense"]) <= 5e-3, (dense_loss.item(), g["parts"]["dense"])
-    for a, b in zip(out["logits"], g["logits"]):
-        assert _cos(a.cpu(), b) > 0.9995
-    for a, b in zip(out["dense_logits"], g["dense_logits"]):
-        assert _cos(a.cpu(), b) > 0.9995
-    params = dict(model.named_parameters())
-    assert set(k for k, p in params.items() if p.grad is not None) == set(g["grads"])
-    worst = []
-    for k, ref in g["grads"].items():
-        mine = params[k].grad.detach().float().reshape(-1).cpu()
-        worst.append((_cos(mine[golden.sample_index(mine.numel())], ref["sample"]), mine.norm().item() / (ref["norm"] + 1e-20), k))
-    worst.sort()
-    txt = "\n".join("cos %.5f normratio %.4f %s" % w for w in worst[:10])
-    assert worst[0][0] > 0.96, txt
-    assert all(0.9 < w[1] < 1.1 for w in worst), txt
