@@ -64,13 +64,15 @@ def filip_inputs(c):
 
 RES_CASES = {
     "clip_res50_l1111_b4": dict(batch=4, layers=(1, 1, 1, 1), t_layers=2, embed_dim=1024, seed=6),
-    "clip_res50_l3463_b32": dict(batch=32, layers=(3, 4, 6, 3), t_layers=12, embed_dim=1024, seed=16),   # configs[3] depth
+    # configs[3] depth; last-BatchNorm gains x0.25 (the reference zero-initialises them): see synth.resnet_state_dict
+    "clip_res50_l3463_b32": dict(batch=32, layers=(3, 4, 6, 3), t_layers=12, embed_dim=1024, seed=16, bn3_scale=0.25),
 }
 
 
 def res_inputs(c):
     from . import synth
-    sd = synth.clip_res_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], layers=c["layers"], t_layers=c["t_layers"])
+    sd = synth.clip_res_state_dict(seed=c["seed"], embed_dim=c["embed_dim"], layers=c["layers"], t_layers=c["t_layers"],
+                                   bn3_scale=c.get("bn3_scale", 1.0))
     return sd, synth.synth_images(c["batch"], seed=c["seed"]), synth.synth_token_ids(c["batch"], seed=c["seed"])
 
 

@@ -181,8 +181,12 @@ def filip_extra_state_dict(seed=0, v_width=768, t_width=512, dense_dim=256, voca
     return sd
 
 
-def resnet_state_dict(seed=0, layers=(3, 4, 6, 3), width=64, embed_dim=1024, res=224, prefix="visual."):
-    """state_dict of ModifiedResNet (modified_resnet.py:109-190) under `prefix`, BatchNorm buffers included."""
+def resnet_state_dict(seed=0, layers=(3, 4, 6, 3), width=64, embed_dim=1024, res=224, prefix="visual.", bn3_scale=1.0):
+    """state_dict of ModifiedResNet (modified_resnet.py:109-190) under `prefix`, BatchNorm buffers included.
+    `bn3_scale` multiplies the gain of every block's last BatchNorm: the reference zero-initialises it
+    (modified_resnet.py:177-180) so that a freshly built 16-block network is a near-identity map; with gains ~1 a RANDOM
+    network of that depth amplifies any perturbation ~1.25x per block (measured: tools/resnet_debug.py) and no reduced-
+    precision implementation can follow its fp32 gradients — full-depth parity cases use a small non-zero gain."""
     sd = {}
 
     def conv(name, cout, cin, k):
@@ -206,6 +210,7 @@ def resnet_state_dict(seed=0, layers=(3, 4, 6, 3), width=64, embed_dim=1024, res
             conv(p + "conv1", planes, inplanes, 1); bn(p + "bn1", planes)
             conv(p + "conv2", planes, planes, 3); bn(p + "bn2", planes)
             conv(p + "conv3", planes * 4, planes, 1); bn(p + "bn3", planes * 4)
+            sd[prefix + p + "bn3.weight"] = sd[prefix + p + "bn3.weight"] * bn3_scale
             if s > 1 or inplanes != planes * 4:
                 conv(p + "downsample.0", planes * 4, inplanes, 1); bn(p + "downsample.1", planes * 4)
             inplanes = planes * 4
@@ -222,9 +227,9 @@ def resnet_state_dict(seed=0, layers=(3, 4, 6, 3), width=64, embed_dim=1024, res
     return sd
 
 
-def clip_res_state_dict(seed=0, embed_dim=1024, layers=(3, 4, 6, 3), t_layers=12):
+def clip_res_state_dict(seed=0, embed_dim=1024, layers=(3, 4, 6, 3), t_layers=12, bn3_scale=1.0):
     """clip_res50 (clip.py:149-156): ModifiedResNet image tower + the text transformer."""
     full = clip_vit_state_dict(seed=seed, embed_dim=embed_dim, v_layers=0, t_layers=t_layers)
     sd = {k: v for k, v in full.items() if not k.startswith("visual.")}
-    sd.update(resnet_state_dict(seed=seed, layers=layers, embed_dim=embed_dim))
+    sd.update(resnet_state_dict(seed=seed, layers=layers, embed_dim=embed_dim, bn3_scale=bn3_scale))
     return sd

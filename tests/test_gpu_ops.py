@@ -281,7 +281,8 @@ def test_fused_adamw_state_dict_and_skipped_params(cuda_dev):
         for p, q in zip(ps, qs):
             p.copy_(q)
     mine = FusedAdamW(ps, lr=1e-3, weight_decay=0.05)
-    mine.load_state_dict(ref.state_dict())                 # tensor-valued `step`
+    import copy
+    mine.load_state_dict(copy.deepcopy(ref.state_dict()))  # tensor-valued `step`; deepcopy: load_state_dict aliases same-device tensors
     for it in range(3):
         for i, (p, q) in enumerate(zip(ps, qs)):
             if it == 1 and i == 2:                         # the third parameter skips one iteration

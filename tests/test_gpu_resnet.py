@@ -175,3 +175,50 @@ def test_res50_wrappers_run(cuda_dev, kind):
     for k, p in model.named_parameters():
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), k
+
+
+@pytest.mark.parametrize("inplanes,planes,stride,H", [(64, 64, 1, 56), (256, 64, 1, 56), (256, 128, 2, 56), (512, 128, 1, 28),
+                                                      (1024, 256, 1, 14), (1024, 512, 2, 14), (2048, 512, 1, 7)])
+def test_bottleneck_block_isolated(cuda_dev, inplanes, planes, stride, H):
+    """ONE Bottleneck (every variant of ModifiedResNet-50: projection / identity shortcut, stride 1 / 2, 56^2 .. 7^2) on
+    the same input as an fp32 torch statement of modified_resnet.py:40-56: output, input gradient and every parameter
+    gradient.  Run in isolation there is no depth for bf16 rounding to compound through, so anything below ~0.999 here
+    would be an indexing error (im2col / col2im / BatchNorm apply), not noise — which the deep-network goldens cannot
+    tell apart (a randomly initialised 16-block network amplifies a 0.5 % perturbation ~1.25x per block)."""
+    import torch.nn.functional as F
+    from declip_b200.model.modified_resnet import Bottleneck
+    torch.manual_seed(inplanes + planes + H)
+    B = 4
+    blk = Bottleneck(inplanes, planes, stride).to(cuda_dev).train()
+    with torch.no_grad():
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    x = torch.relu(torch.randn(B, inplanes, H, H, device=cuda_dev) + 0.3)
+    xh = x.permute(0, 2, 3, 1).reshape(-1, inplanes).contiguous().bfloat16().requires_grad_(True)
+    xr = xh.detach().float().view(B, H, H, inplanes).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    y, h2, w2 = blk.run(xh, B, H, H)
+    g = torch.randn(B, planes * 4, h2, w2, device=cuda_dev)
+    y.backward(g.permute(0, 2, 3, 1).reshape(-1, planes * 4).contiguous().bfloat16())
+    mine = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
+    # fp32 statement with the same parameters
+    P = {k: p.detach().clone().requires_grad_(True) for k, p in blk.named_parameters()}
+
+    def bn(t, n):
+        return F.batch_norm(t, None, None, P[n + ".weight"], P[n + ".bias"], True, 0.1, 1e-5)
+    o = F.relu(bn(F.conv2d(xr, P["conv1.weight"]), "bn1"))
+    o = F.relu(bn(F.conv2d(o, P["conv2.weight"], padding=1), "bn2"))
+    if stride > 1:
+        o = F.avg_pool2d(o, stride)
+    o = bn(F.conv2d(o, P["conv3.weight"]), "bn3")
+    idn = xr
+    if blk.downsample is not None:
+        idn = bn(F.conv2d(F.avg_pool2d(xr, stride) if stride > 1 else xr, P["downsample.0.weight"]), "downsample.1")
+    ref = F.relu(o + idn)
+    ref.backward(g.bfloat16().float())
+    torch.cuda.synchronize()
+    assert _cos(_nchw(y, B, h2, w2), ref) > 0.9999
+    assert _cos(_nchw(xh.grad, B, H, H), xr.grad) > 0.999
+    for k, gref in P.items():
+        assert _cos(mine[k], gref.grad) > (0.995 if ".bn" in "." + k or "downsample.1" in k else 0.999), (k, _cos(mine[k], gref.grad))
