@@ -18,7 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="clip")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--top", type=int, default=32)
-ap.add_argument("--head", default="strips")
+ap.add_argument("--head", default="fused")
 args = ap.parse_args()
 b = args.batch
 dev = torch.device("cuda:0")
