@@ -222,10 +222,11 @@ TOL = {
     # ModifiedResNet-50: bf16 activation storage flips ReLU gates — a bf16-ROUNDED copy of the reference's own fp32 math
     # reaches only ~0.90 median / 0.74 worst gradient cosine (profiles/r02_resnet_bf16_noise.md); block-level exactness is
     # asserted separately (tests/test_gpu_resnet.py::test_bottleneck_block_isolated)
-    "res": dict(hi=dict(dloss=2e-2, bn_stats_rel_max=3e-2, grad_zero_max_abs=1e-3),
-                lo=dict(logits_cos=0.999, grad_cos_min=0.6, grad_cos_p10=0.8, grad_norm_ratio_min=0.8,
-                        grad_sparse_norm_ratio_min=0.8),
-                hi2=dict(grad_norm_ratio_max=1.25, grad_sparse_norm_ratio_max=1.25)),
+    # measured at the real (3,4,6,3) depth, b = 32: |d loss| 7.5e-4, logits cos 0.99993, gradient cos min 0.768 / p10 0.874
+    "res": dict(hi=dict(dloss=5e-3, bn_stats_rel_max=1.5e-2, grad_zero_max_abs=1e-3),
+                lo=dict(logits_cos=0.9995, grad_cos_min=0.6, grad_cos_p10=0.8, grad_norm_ratio_min=0.8,
+                        grad_sparse_norm_ratio_min=0.9),
+                hi2=dict(grad_norm_ratio_max=1.25, grad_sparse_norm_ratio_max=1.1)),
 }
 
 

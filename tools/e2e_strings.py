@@ -2,7 +2,10 @@
 `model({'images': ..., 'captions': [[str], ...]})` (clip.py:118-127): host C++ BPE tokenisation inside
 TextTransformer.forward, H2D copies of the images from pinned memory, forward + ClipInfoCELoss + backward + FusedAdamW.
 The real merges table is a download the reference does not ship, so the 277-merge test table and captions over its toy
-vocabulary are used — the kernels see the same shapes.  Usage (GPU box): python tools/e2e_strings.py [steps]"""
+vocabulary are used — the kernels see the same shapes.  Three legs: (a) strings tokenised inside forward (pinned ids,
+asynchronous H2D), (b) the same batches through declip_b200.tokenizer.CaptionPipeline (worker thread tokenises and uploads
+step i+1 while the device runs step i), (c) pre-tokenised ids resident on the device (the bench's `value` path).
+Usage (GPU box): python tools/e2e_strings.py [steps]"""
 import json
 import os
 import random
@@ -51,6 +54,26 @@ def step(i):
     loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
 
 
+def step_inputs(inp, i):
+    li, lt = model(inp)
+    loss, _ = crit(li, lt)
+    loss.backward()
+    opt.step()
+    model.logit_scale.data.clamp_(3.0, 6.0)
+    opt.zero_grad(set_to_none=True)
+    loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+
+
+def timed(fn, n):
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s_.record()
+    fn(n)
+    e_.record()
+    torch.cuda.synchronize()
+    return s_.elapsed_time(e_) / n
+
+
 for i in range(3):
     step(i)
 torch.cuda.synchronize()
@@ -65,6 +88,37 @@ for i in range(steps):
 e_ev.record()
 torch.cuda.synchronize()
 ms = s_ev.elapsed_time(e_ev) / steps
+# (b) CaptionPipeline: host text work + uploads of step i+1 overlap the device work of step i
+from declip_b200.tokenizer import CaptionPipeline  # noqa: E402
+
+
+def batches(n):
+    for i in range(n):
+        yield {"images": host[i % 2], "captions": caps[i % 2]}
+
+
+def run_pipeline(n):
+    for i, inp in enumerate(CaptionPipeline(batches(n), tok, dev)):
+        step_inputs(inp, i)
+
+
+run_pipeline(3)
+ms_pipe = timed(run_pipeline, steps)
+# (c) ids resident on the device
+ids_dev = [tok.tokenize([c[0] for c in caps[s]], 77).to(dev) for s in range(2)]
+imgs_dev = [h.to(dev) for h in host]
+
+
+def run_ids(n):
+    for i in range(n):
+        step_inputs({"images": imgs_dev[i % 2], "captions": None, "token_ids": ids_dev[i % 2]}, i)
+
+
+run_ids(3)
+ms_ids = timed(run_ids, steps)
 print(json.dumps({"e2e_from_strings_pairs_per_s": round(b / ms * 1e3), "ms_per_step": round(ms, 2), "steps": steps,
+                  "pipeline_pairs_per_s": round(b / ms_pipe * 1e3), "pipeline_ms_per_step": round(ms_pipe, 2),
+                  "resident_ids_pairs_per_s": round(b / ms_ids * 1e3), "resident_ids_ms_per_step": round(ms_ids, 2),
+                  "strings_vs_ids": round(ms_ids / ms, 4), "pipeline_vs_ids": round(ms_ids / ms_pipe, 4),
                   "host_tokenize_ms_per_512_captions": round(t_tok * 1e3, 2), "h2d_bytes_per_step": b * 3 * 224 * 224 * 4 + b * 77 * 8,
                   "tokenizer": "C++ BPE (dc_bpe_tokenize), 277-merge test table", "last_loss": float(loss_host[steps + 2])}))
