@@ -8,7 +8,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_C.so")
+_SO = os.environ.get("DECLIP_B200_LIB") or os.path.join(_HERE, "_C.so")     # override: A/B builds of the same ABI
 
 _lib = None
 _lock = threading.Lock()

@@ -17,12 +17,17 @@
 namespace dc {
 
 constexpr int BN2 = 256;
-constexpr int G2_STAGES = 6;
+#ifndef DC_G2_EPI_BUFS
+#define DC_G2_EPI_BUFS 2
+#endif
+constexpr int G2_EPI_BUFS = DC_G2_EPI_BUFS;      // rotating 2 KiB output staging buffers per epilogue warp (4 buffers + 5 stages
+                                                 // measured 1 % SLOWER than 2 + 6: profiles/r02_gemm_perf_v3_bufs_ab.md)
+constexpr int G2_STAGES = G2_EPI_BUFS == 4 ? 5 : 6;   // the deeper store staging costs one of the six 32 KiB operand stages
 constexpr int G2_A_BYTES = BM * BK * 2;          // 16 KiB: this CTA's 128 rows
 constexpr int G2_B_BYTES = (BN2 / 2) * BK * 2;   // 16 KiB: this CTA's half of the 256 N rows
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_TMEM_COLS = 2 * BN2;
-constexpr int G2_STAGING_BYTES = EPI_WARPS * 4096;   // 2 x (32x32 bf16) per epilogue warp
+constexpr int G2_STAGING_BYTES = EPI_WARPS * G2_EPI_BUFS * 2048;   // G2_EPI_BUFS x (32x32 bf16) per epilogue warp
 constexpr int G2_BIAS_BYTES = 0;                      // bias is broadcast by warp shuffles
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_STAGING_BYTES + 256 + G2_BIAS_BYTES + 1024;
 
@@ -214,7 +219,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     constexpr int NCH = BN2 / 64;
-    uint8_t* stage_buf = staging + (warp - 4) * 4096;
+    uint8_t* stage_buf = staging + (warp - 4) * (G2_EPI_BUFS * 2048);
     uint32_t sidx = 0;
     const float alpha = p.alpha * (p.alpha_dev != nullptr ? __ldg(p.alpha_dev) : 1.0f);
     int as = 0;
@@ -229,14 +234,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                              static_cast<uint32_t>(as * BN2 + half * (BN2 / 2));
 #define DC_EPI_CASE(E) \
-  case E: epilogue_tile<E, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf, &tfull_bar[as], aphase); break
+  case E: epilogue_tile<E, NCH, G2_EPI_BUFS>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf, &tfull_bar[as], aphase); break
       switch (p.epi) {
         DC_EPI_CASE(DC_EPI_BF16);
         DC_EPI_CASE(DC_EPI_BF16_GELU);
         DC_EPI_CASE(DC_EPI_BF16_RESID);
         DC_EPI_CASE(DC_EPI_BF16_DGELU);
         DC_EPI_CASE(DC_EPI_F32);
-        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf,
+        default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH, G2_EPI_BUFS>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf,
                                                        &tfull_bar[as], aphase); break;
       }
 #undef DC_EPI_CASE

@@ -36,15 +36,16 @@ constexpr int EPI_WARPS = 8;
 // TMA store per 32x32 chunk: fully coalesced 64-byte row segments, OOB rows/cols clipped by the TMA unit, and the
 // LSU is free for the next chunk.  fp32 outputs (logit strips, features, split-K wgrad atomics) are written
 // directly.  The epilogue mode is a compile-time parameter (one branch per tile).
+template <int BUFS>
 __device__ __forceinline__ void stage_store_chunk(const float (&v)[32], uint8_t* stage, uint32_t& sidx,
                                                   const CUtensorMap* tm, int col0, int row0) {
   const int lane = lane_id();
-  // two 2 KiB staging buffers per warp: the store issued two chunks ago (same buffer) must have been read out,
-  // the previous one (other buffer) may still be in flight
-  if (lane == 0) bulk_wait_read1();
+  // BUFS rotating 2 KiB staging buffers per warp: the store issued BUFS chunks ago (same buffer) must have been read
+  // out, the BUFS - 1 younger ones may still be in flight
+  if (lane == 0) bulk_wait_read<BUFS - 1>();
   __syncwarp();
-  stage += (sidx & 1u) * 2048;
-  sidx ^= 1u;
+  stage += (sidx & (BUFS - 1)) * 2048;
+  sidx = (sidx + 1) & (BUFS - 1);
   uint8_t* rowp = stage + lane * 64;
   const int sw = (lane >> 1) & 3;    // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
 #pragma unroll
@@ -78,11 +79,12 @@ __device__ __forceinline__ void aux_fetch(const GemmKParams& p, int row0, int co
     if (row < p.M && col < p.N) a[r8] = *reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ldaux + col);
   }
 }
+template <int BUFS>
 __device__ __forceinline__ void aux_transpose(uint4 (&a)[4], uint8_t* stage, uint32_t sidx) {
   const int lane = lane_id();
-  if (lane == 0) bulk_wait_read1();        // the TMA store issued two chunks ago from this buffer has been read out
+  if (lane == 0) bulk_wait_read<BUFS - 1>();        // the TMA store issued BUFS chunks ago from this buffer has been read out
   __syncwarp();
-  uint8_t* buf = stage + (sidx & 1u) * 2048;
+  uint8_t* buf = stage + (sidx & (BUFS - 1)) * 2048;
 #pragma unroll
   for (int r8 = 0; r8 < 4; ++r8) {
     const int rr = (lane >> 2) + 8 * r8;
@@ -113,7 +115,7 @@ __device__ __forceinline__ float chunk_colsum(float (&v)[32]) {
 }
 
 // Waits for the accumulator, then drains this warp's 32 rows x (NCH * 32) columns starting at column `colbase`.
-template <int EPI, int NCH>
+template <int EPI, int NCH, int BUFS = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tm_out, const CUtensorMap* tm_out2,
                                               float alpha, uint32_t taddr, int row0, int colbase, uint32_t& sidx,
                                               uint8_t* stage, uint64_t* tfull, uint32_t parity) {
@@ -145,7 +147,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
     for (int g = 0; g < 4; ++g) axn[g] = make_uint4(0u, 0u, 0u, 0u);
     if (HAS_AUX && c + 1 < NCH) aux_fetch(p, row0, col0 + 32, axn);
     if (col0 < p.N) {  // warp-uniform
-      if (HAS_AUX) aux_transpose(ax, stage, sidx);     // coalesced fetch -> one row per lane
+      if (HAS_AUX) aux_transpose<BUFS>(ax, stage, sidx);     // coalesced fetch -> one row per lane
       uint32_t r[32];
       tmem_ld32(taddr + static_cast<uint32_t>(c * 32), r);
       tmem_ld_wait();
@@ -180,11 +182,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
       }
       if (OUT_BF16) {
         if (EPI == DC_EPI_BF16_GELU) {
-          stage_store_chunk(v, stage, sidx, tm_out2, col0, row0);   // pre-activation u (saved for backward)
+          stage_store_chunk<BUFS>(v, stage, sidx, tm_out2, col0, row0);   // pre-activation u (saved for backward)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
         }
-        stage_store_chunk(v, stage, sidx, tm_out, col0, row0);
+        stage_store_chunk<BUFS>(v, stage, sidx, tm_out, col0, row0);
         if (p.colsum != nullptr) {                            // fused bias gradient: colsum += sum_rows out
           if (!row_ok) {
 #pragma unroll
