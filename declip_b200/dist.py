@@ -12,9 +12,11 @@ overlapping the backward of the remaining layers and of the other tower.  bf16 o
 (302 MB instead of 605 MB per step for CLIP ViT-B/32); the fp32 master gradients stay local.  Only the last
 bucket of the tower that finishes last (its first layers + embeddings) is exposed.
 
-While buckets are in flight the persistent GEMM / attention kernels leave `sm_reserve` SMs free
-(dc_set_sm_reserve) so NCCL's CTAs (capped to the same number on a dedicated communicator) never queue behind a
-whole persistent tile loop — without it every GEMM that overlaps a collective waits a full extra wave.
+Optional (`nccl_ctas` > 0, off by default): a dedicated communicator capped to that many CTAs plus
+`dc_set_sm_reserve(nccl_ctas)`, so that the persistent GEMM / attention kernels leave exactly the SMs NCCL occupies.
+Measured on 2 x B200 (profiles/r02_scaling_variants_n2.md): it LOSES — reserving 8 SMs for the whole backward costs
+more (30.7 ms/step) than the occasional extra wave it avoids (29.5 without, same buckets); fewer, larger buckets win
+(6 layers per bucket: 28.6 ms; 3 layers: 29.5; one per tower: 28.8; N = 1: 27.4-28.0).
 """
 import ctypes
 import os
@@ -45,12 +47,12 @@ class DistModule(Module):
         super().__init__()
         self.module = module
         self.sync = sync
-        self.bucket_layers = int(os.environ.get("DECLIP_B200_BUCKET_LAYERS", "3")) if bucket_layers is None else bucket_layers
+        self.bucket_layers = int(os.environ.get("DECLIP_B200_BUCKET_LAYERS", "6")) if bucket_layers is None else bucket_layers
         grad_dtype = grad_dtype or os.environ.get("DECLIP_B200_GRAD_DTYPE", "bf16")
         if grad_dtype not in ("bf16", "fp32"):
             raise ValueError("grad_dtype must be 'bf16' or 'fp32'")
         self.grad_bf16 = grad_dtype == "bf16"
-        self.nccl_ctas = int(os.environ.get("DECLIP_B200_NCCL_CTAS", "8")) if nccl_ctas is None else nccl_ctas
+        self.nccl_ctas = int(os.environ.get("DECLIP_B200_NCCL_CTAS", "0")) if nccl_ctas is None else nccl_ctas
         self._pending = []        # (rt id, covered parameter ids, side-stream event) of buckets launched during backward
         self._sent = {}           # id(rt) -> lowest layer whose gradients are already on the wire
         self._side = None
