@@ -83,21 +83,27 @@ def weight_shadow(p, pad_rows=0):
 # clusters = 4.05 waves for every N = 768 output).  Issued on two streams, the CTAs of one tower's next kernel occupy
 # the SMs the other tower's tail wave leaves free — late-starting CTAs are the high-numbered ones, which own one tile
 # less, so the static tile schedules balance by themselves.
-#   forward : inside `with concurrent_towers():` the FIRST tower runtime that runs goes to the side stream (it forks
-#             before the main stream has any tower work queued); the region's exit joins.
-#   backward: the FIRST tower runtime whose backward node autograd executes goes to the side stream (its incoming
-#             gradient only waits for the head's backward); an end-of-backward callback joins.
+#   Inside `with concurrent_towers():` the FIRST tower runtime that runs is applied under a side stream (it forks
+#   before the main stream has any tower work queued); the region's exit joins.  Autograd runs a node's backward on
+#   the stream its forward was applied on and orders it after the event recorded when its incoming gradient was
+#   produced (the head's backward) — so the same tower runs on the side stream in the backward too, concurrently with
+#   the other tower on the main stream, and its multi-GB workspace is allocated, used and freed on ONE stream (a
+#   cross-stream `record_stream` on it made the caching allocator unable to reuse the block in time: intermittent
+#   40 ms steps while it grew the pool with cudaMalloc).  Parameter gradients are written by raw kernels, not by
+#   autograd, so an end-of-backward callback joins the side stream into the stream `backward()` was called on.
 TOWER_STREAMS = os.environ.get("DECLIP_B200_TOWER_STREAMS", "1") != "0"
 _tls = threading.local()
+_side_streams = {}
+_side_lock = threading.Lock()
 
 
 def _side_stream(dev):
-    pool = getattr(_tls, "side", None)
-    if pool is None:
-        pool = _tls.side = {}
-    if dev not in pool:
-        pool[dev] = torch.cuda.Stream(device=dev)
-    return pool[dev]
+    dev = torch.device(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _side_lock:
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(device=dev)
+        return _side_streams[key]
 
 
 class concurrent_towers:
@@ -106,16 +112,15 @@ class concurrent_towers:
     def __enter__(self):
         self.prev = getattr(_tls, "region", None)
         _tls.region = self if TOWER_STREAMS else None
-        self.side_rt, self.outputs, self.stream, self.dev = None, [], None, None
+        self.side_rt, self.outputs, self.stream, self.dev, self.main = None, [], None, None, None
         return self
 
     def __exit__(self, *exc):
         _tls.region = self.prev
         if self.stream is not None:
-            main = torch.cuda.current_stream(self.dev)
-            main.wait_stream(self.stream)
-            for t in self.outputs:              # allocated on the side stream's pool, consumed on the main stream
-                t.record_stream(main)
+            self.main.wait_stream(self.stream)
+            for t in self.outputs:              # small tensors allocated on the side stream's pool, consumed on the main stream
+                t.record_stream(self.main)
         return False
 
     def stream_for(self, rt, dev):
@@ -123,32 +128,20 @@ class concurrent_towers:
         if self.side_rt is None:
             self.side_rt, self.dev = rt, dev
             self.stream = _side_stream(dev)
-            self.stream.wait_stream(torch.cuda.current_stream(dev))      # inputs produced on the main stream
+            self.main = torch.cuda.current_stream(dev)
+            self.stream.wait_stream(self.main)      # inputs produced on the main stream
         return self.stream if rt is self.side_rt else None
 
 
-class _BackwardPass:
-    """Per-backward-pass stream assignment (reset by an autograd end-of-backward callback)."""
-
-    def __init__(self):
-        self.side_rt, self.stream, self.dev = None, None, None
-
-    def stream_for(self, rt, dev):
-        if self.side_rt is None:
-            self.side_rt, self.dev = rt, dev
-            self.stream = _side_stream(dev)
-            self.main = torch.cuda.current_stream(dev)     # autograd runs the node on the stream its forward was applied on
-            self.stream.wait_stream(self.main)             # the head's backward produced d(features)
-            torch.autograd.Variable._execution_engine.queue_callback(self.finish)
-        return self.stream if rt is self.side_rt else None
-
-    def finish(self):
-        _tls.bwd = None
-        if self.stream is not None:
-            self.main.wait_stream(self.stream)
-            cur = torch.cuda.current_stream(self.dev)
-            if cur != self.main:
-                cur.wait_stream(self.stream)
+def _join_side_after_backward(side, main):
+    """Queue the join of the side stream into `main` (and into whatever stream is current when the engine finishes).
+    One callback per tower node: a handful per step, and a repeated wait on an already-joined stream is free."""
+    def finish():
+        main.wait_stream(side)
+        cur = torch.cuda.current_stream(side.device)
+        if cur != main and cur != side:
+            cur.wait_stream(side)
+    torch.autograd.Variable._execution_engine.queue_callback(finish)
 
 
 class TowerRuntime:
@@ -403,9 +396,15 @@ class _TowerFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rt, inp, anchor, dense, pre=False):
         params = rt._params()
-        outs, (inp_used, cfg, ws) = _forward_on_stream(rt, inp, params, dense, pre)
+        feats, inp_used, cfg, ws, words = rt.forward(inp, params, dense)      # on the stream run_tower applied us under
+        outs = [feats]
+        if dense:
+            outs.append(words)
+        if pre:
+            outs.append(rt.pre_features(cfg, ws).float())
         rt._outstanding += 1
         ctx.rt, ctx.cfg, ctx.inp, ctx.ws, ctx.params, ctx.dense, ctx.pre = rt, cfg, inp_used, ws, params, dense, pre
+        ctx.streams = getattr(_tls, "apply_streams", None)        # (side, main) when applied under the side stream
         return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
@@ -414,23 +413,17 @@ class _TowerFunction(torch.autograd.Function):
         rest = list(rest)
         dwords = rest.pop(0) if ctx.dense else None
         dpre = rest.pop(0) if ctx.pre else None
-        stream = None
-        if TOWER_STREAMS:
-            bp = getattr(_tls, "bwd", None)
-            if bp is None:
-                bp = _tls.bwd = _BackwardPass()
-            stream = bp.stream_for(rt, ctx.ws.device)
-        with (torch.cuda.stream(stream) if stream is not None else _NullCtx()):
-            if stream is not None:
-                ctx.ws.record_stream(stream)            # allocated on another stream's pool in the forward
-                for t in (dfeats, dwords, dpre, ctx.inp):
-                    if t is not None:
-                        t.record_stream(stream)
-            rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords, dpre)
-            ctx.ws = None
-            rt._outstanding = max(0, rt._outstanding - 1)
-            if rt._outstanding == 0 and rt.grad_ready_hook is not None:
-                rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
+        if ctx.streams is not None:     # the engine runs this node on the side stream it was applied under
+            side, main = ctx.streams
+            for t in (dfeats, dwords, dpre):
+                if t is not None:
+                    t.record_stream(side)           # small gradients produced on the main stream
+            _join_side_after_backward(side, main)
+        rt.backward(ctx.cfg, ctx.inp, ctx.ws, dfeats, ctx.params, ctx.dense, dwords, dpre)
+        ctx.ws = None
+        rt._outstanding = max(0, rt._outstanding - 1)
+        if rt._outstanding == 0 and rt.grad_ready_hook is not None:
+            rt.grad_ready_hook(rt)      # e.g. DistModule: start this tower's gradient all-reduce now, overlapped
         return None, None, None, None, None
 
 
@@ -442,6 +435,19 @@ def run_tower(rt, inp, dense=False, pre=False):
     if torch.is_grad_enabled():
         anchor = next((p for p in params.values() if p.requires_grad), None)
         if anchor is not None:
-            return _TowerFunction.apply(rt, inp, anchor, dense, pre)
+            region = getattr(_tls, "region", None)
+            stream = region.stream_for(rt, inp.device) if region is not None and inp.is_cuda else None
+            if stream is None:
+                _tls.apply_streams = None
+                return _TowerFunction.apply(rt, inp, anchor, dense, pre)
+            inp.record_stream(stream)
+            _tls.apply_streams = (stream, region.main)
+            try:
+                with torch.cuda.stream(stream):
+                    out = _TowerFunction.apply(rt, inp, anchor, dense, pre)
+            finally:
+                _tls.apply_streams = None
+            region.outputs.extend(out if isinstance(out, tuple) else (out,))
+            return out
     outs, _ = _forward_on_stream(rt, inp, params, dense, pre)
     return outs[0] if len(outs) == 1 else tuple(outs)
