@@ -515,6 +515,8 @@ def run_native(args):
                        "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch, "
                        "rewrites the bf16 GEMM shadows)", "l2": "inputs+activations >> 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "memory": {"peak_allocated_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                       "peak_reserved_gb": round(torch.cuda.max_memory_reserved() / 2 ** 30, 1)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
