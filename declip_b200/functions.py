@@ -754,6 +754,42 @@ class HeadInfo:
         return self.ws[self.layout.out + 5:self.layout.out + 6]
 
 
+class _SymmFeatures:
+    """Per-rank bf16 feature rows in SYMMETRIC memory (torch.distributed._symmetric_memory): every rank's buffer is
+    mapped into every process, so the head kernels read the peers' rows straight over NVLink through one TMA tensor map
+    per rank (dc_head_args.n_src = world) and the forward needs no all-gather collective at all — only a device-side
+    barrier after the rows are written.  Two buffers alternate: the backward of step i re-reads buffer i % 2 while no
+    rank can reach the prepare of step i + 2 (which overwrites it) before every rank has passed the barrier of step
+    i + 1, i.e. has finished enqueueing its step-i backward."""
+
+    _cache = {}
+
+    def __init__(self, b, ld, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.bufs = [symm_mem.empty((b, ld), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.hdls = [symm_mem.rendezvous(t, dist.group.WORLD) for t in self.bufs]
+        self.ptrs = [[int(p) for p in h.buffer_ptrs] for h in self.hdls]
+        self.i = 0
+
+    @classmethod
+    def get(cls, b, ld, dev):
+        key = (b, ld, str(dev))
+        if key not in cls._cache:
+            cls._cache[key] = cls(b, ld, dev)
+        return cls._cache[key]
+
+    def next(self):
+        k = self.i & 1
+        self.i += 1
+        return self.bufs[k], self.hdls[k], self.ptrs[k]
+
+
+def symm_head_enabled(b):
+    """Peer-memory feature exchange for the fused head: opt-in (DECLIP_B200_SYMM_HEAD=1) — needs b % 256 == 0."""
+    import os
+    return os.environ.get("DECLIP_B200_SYMM_HEAD", "0") == "1" and b % 256 == 0
+
+
 class FusedClipHead(torch.autograd.Function):
     """parts[2], workspace = fused CLIP head on the raw tower outputs (image_features, text_features fp32 [b, E]).
     Exchange steps when gathering: one bf16 feature all-gather in the forward, one all-gather of 2b+2 floats per rank
@@ -772,8 +808,14 @@ class FusedClipHead(torch.autograd.Function):
         dev = img.device
         L = HeadLayout.get(lib, b, e)
         ws = torch.empty(L.total, device=dev, dtype=torch.float32)
-        allb = torch.empty(n, 2 * e, device=dev, dtype=torch.bfloat16)
-        local = allb[row0:row0 + b]
+        symm = gather and symm_head_enabled(b)
+        if symm:
+            local, hdl, srcs = _SymmFeatures.get(b, 2 * e, dev).next()
+            allb = local
+        else:
+            allb = torch.empty(n, 2 * e, device=dev, dtype=torch.bfloat16)
+            local = allb[row0:row0 + b]
+            srcs = [allb.data_ptr()]
         ls = logit_scale.detach()
         if ls.dtype != torch.float32 or not ls.is_cuda:
             raise RuntimeError("declip_b200: logit_scale must be an fp32 CUDA parameter")
@@ -781,12 +823,15 @@ class FusedClipHead(torch.autograd.Function):
         eps = (ctypes.c_float * 2)(0.0, 1e-10)                                         # clip.py:129-130
         _lib.check(lib.dc_head_prepare(feats, eps, 2, b, e, _PTR(local.data_ptr()), _PTR(ws.data_ptr()), _PTR(ls.data_ptr()),
                                        100.0 if clamp else float("inf"), _stream()), "dc_head_prepare")
-        if gather:
+        if symm:
+            hdl.barrier(channel=0)                                                     # every rank's rows are written
+        elif gather:
             dist.all_gather_into_tensor(allb, local)                                  # in place: `local` is rank's slice
-        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), [allb.data_ptr()], ws.data_ptr())
+        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), srcs, ws.data_ptr())
         _lib.check(lib.dc_head_forward(ctypes.byref(args), _stream()), "dc_head_forward")
         ctx.save_for_backward(img, txt, ws, allb)
         ctx.meta = (b, n, e, row0, gather, world, L)
+        ctx.srcs = srcs
         parts = ws[L.out:L.out + 2].clone()      # its own storage: an autograd output must not alias the workspace
         ctx.mark_non_differentiable(ws)
         return parts, ws
@@ -804,8 +849,8 @@ class FusedClipHead(torch.autograd.Function):
         else:
             exch = ws[L.lse:L.lse + 2 * b + 2]
         d_img, d_txt = torch.empty_like(img), torch.empty_like(txt)
-        local = allb[row0:row0 + b]
-        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), [allb.data_ptr()], ws.data_ptr())
+        local = allb if len(ctx.srcs) > 1 else allb[row0:row0 + b]
+        args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), ctx.srcs, ws.data_ptr())
         xraw = (_PTR * 2)(img.data_ptr(), txt.data_ptr())
         eps = (ctypes.c_float * 2)(0.0, 1e-10)
         dxo = (_PTR * 2)(d_img.data_ptr(), d_txt.data_ptr())
