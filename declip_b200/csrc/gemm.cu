@@ -192,6 +192,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         DC_EPI_CASE(DC_EPI_BF16_RESID);
         DC_EPI_CASE(DC_EPI_BF16_DGELU);
         DC_EPI_CASE(DC_EPI_F32);
+        DC_EPI_CASE(DC_EPI_F32_GROUPMAX16);
         default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage,
                                                        &tfull_bar[as], aphase); break;
       }
@@ -235,7 +236,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error("gemm: empty problem");
   if ((a.N & 7) || (a.lda & 7) || (a.ldb & 7) || (a.ldo & 3)) return set_error("gemm: N, lda, ldb must be multiples of 8");
-  if (a.epilogue < 0 || a.epilogue > DC_EPI_F32_ATOMIC) return set_error("gemm: bad epilogue");
+  if (a.epilogue < 0 || a.epilogue > DC_EPI_F32_GROUPMAX16) return set_error("gemm: bad epilogue");
+  if (a.epilogue == DC_EPI_F32_GROUPMAX16 && (a.out2 == nullptr || (a.N & 15)))
+    return set_error("gemm: the group-max epilogue needs out2 (arg-max bytes) and N % 16 == 0");
   if ((a.epilogue == DC_EPI_BF16_RESID || a.epilogue == DC_EPI_BF16_DGELU) && a.aux == nullptr)
     return set_error("gemm: epilogue needs aux");
   if (a.epilogue == DC_EPI_BF16_GELU && a.out2 == nullptr) return set_error("gemm: GELU epilogue needs out2");

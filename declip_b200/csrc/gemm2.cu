@@ -241,6 +241,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         DC_EPI_CASE(DC_EPI_BF16_RESID);
         DC_EPI_CASE(DC_EPI_BF16_DGELU);
         DC_EPI_CASE(DC_EPI_F32);
+        DC_EPI_CASE(DC_EPI_F32_GROUPMAX16);
         default: epilogue_tile<DC_EPI_F32_ATOMIC, NCH, G2_EPI_BUFS>(p, &tmOut, &tmOut2, alpha, taddr, row0, colbase, sidx, stage_buf,
                                                        &tfull_bar[as], aphase); break;
       }

@@ -120,7 +120,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
                                               float alpha, uint32_t taddr, int row0, int colbase, uint32_t& sidx,
                                               uint8_t* stage, uint64_t* tfull, uint32_t parity) {
   constexpr bool HAS_AUX = (EPI == DC_EPI_BF16_RESID || EPI == DC_EPI_BF16_DGELU);
-  constexpr bool HAS_BIAS = (EPI != DC_EPI_F32_ATOMIC && EPI != DC_EPI_BF16_DGELU);
+  constexpr bool HAS_BIAS = (EPI != DC_EPI_F32_ATOMIC && EPI != DC_EPI_BF16_DGELU && EPI != DC_EPI_F32_GROUPMAX16);
+  constexpr bool GMAX = (EPI == DC_EPI_F32_GROUPMAX16);
+  float gbest[GMAX ? 2 * NCH : 1];
+  int garg[GMAX ? 2 * NCH : 1];
   constexpr bool OUT_BF16 = (EPI <= DC_EPI_BF16_DGELU);
   const int lane = lane_id();
   const int row = row0 + lane;
@@ -195,6 +198,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
           const float cs = chunk_colsum(v);
           if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, cs);
         }
+      } else if (GMAX) {
+        // max / arg-max over each group of 16 consecutive columns (two groups per 32-column chunk), kept in registers
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float best = v[16 * h];
+          int bi = 0;
+#pragma unroll
+          for (int m = 1; m < 16; ++m)
+            if (v[16 * h + m] > best) { best = v[16 * h + m]; bi = m; }
+          gbest[GMAX ? 2 * c + h : 0] = best;
+          garg[GMAX ? 2 * c + h : 0] = bi;
+        }
       } else if (row_ok) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -218,6 +233,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) ax[g] = axn[g];
+  }
+  if (GMAX && row_ok) {
+    const int groups = p.N >> 4;
+    float* o = static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo;
+    uint8_t* a = static_cast<uint8_t*>(p.out2) + static_cast<size_t>(row) * p.ldo2;
+#pragma unroll
+    for (int g = 0; g < 2 * NCH; ++g) {
+      const int gi = (colbase >> 4) + g;
+      if (gi < groups) {
+        o[gi] = gbest[GMAX ? g : 0];
+        a[gi] = static_cast<uint8_t>(garg[GMAX ? g : 0]);
+      }
+    }
   }
 }
 

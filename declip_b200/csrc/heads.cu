@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) groupmax_mean_fwd_kernel(const float* __r
         if (v > best) { best = v; bi = m; }
       }
       acc += best;
-      arg[(static_cast<size_t>(i) * n + j) * ncand + l] = static_cast<uint8_t>(bi);
+      if (arg != nullptr) arg[(static_cast<size_t>(i) * n + j) * ncand + l] = static_cast<uint8_t>(bi);
     }
   }
   s_part[threadIdx.y][threadIdx.x] = acc;

@@ -600,11 +600,18 @@ class FilipLate(torch.autograd.Function):
         batch = d.shape[0] // n
         ncand = sel.shape[0] // group
         s = logit_scale_dense.detach().float().exp().reshape(1)
-        G = ops.gemm(d16, sel16, epilogue=ops.EPI_F32, alpha_dev=s)                      # [B*n, N*group]
         out = torch.empty(batch, ncand, device=d.device, dtype=torch.float32)
-        arg = torch.empty(batch * n, ncand, device=d.device, dtype=torch.uint8)
-        _lib.check(lib.dc_groupmax_mean_fwd(_PTR(G.data_ptr()), G.stride(0), batch, n, group, ncand, _PTR(out.data_ptr()),
-                                            out.stride(0), _PTR(arg.data_ptr()), _stream()), "dc_groupmax_mean_fwd")
+        if group == 16:
+            # fused: the GEMM epilogue reduces every group of 16 score columns to (max, arg-max) straight out of TMEM —
+            # the [B*n, N*16] score matrix (6.6 + 10.3 GB fp32 at N = 4096) is never written
+            mx, arg = ops.gemm(d16, sel16, epilogue=ops.EPI_F32_GROUPMAX16, alpha_dev=s)      # [B*n, N] fp32 / uint8
+            _lib.check(lib.dc_groupmax_mean_fwd(_PTR(mx.data_ptr()), mx.stride(0), batch, n, 1, ncand, _PTR(out.data_ptr()),
+                                                out.stride(0), None, _stream()), "dc_groupmax_mean_fwd")
+        else:
+            G = ops.gemm(d16, sel16, epilogue=ops.EPI_F32, alpha_dev=s)                      # [B*n, N*group]
+            arg = torch.empty(batch * n, ncand, device=d.device, dtype=torch.uint8)
+            _lib.check(lib.dc_groupmax_mean_fwd(_PTR(G.data_ptr()), G.stride(0), batch, n, group, ncand, _PTR(out.data_ptr()),
+                                                out.stride(0), _PTR(arg.data_ptr()), _stream()), "dc_groupmax_mean_fwd")
         ctx.save_for_backward(d16, sel16, arg, s, out)
         ctx.meta = (batch, n, group, ncand)
         return out

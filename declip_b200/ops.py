@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs
 
-EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_BF16_DGELU, EPI_F32, EPI_F32_ATOMIC = range(6)
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESID, EPI_BF16_DGELU, EPI_F32, EPI_F32_ATOMIC, EPI_F32_GROUPMAX16 = range(7)
 
 
 def _ptr(t):
@@ -46,7 +46,14 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1
     else:
         N, Kb = b.shape
     assert K == Kb, "contraction mismatch %d vs %d" % (K, Kb)
-    f32_out = epilogue in (EPI_F32, EPI_F32_ATOMIC)
+    f32_out = epilogue in (EPI_F32, EPI_F32_ATOMIC, EPI_F32_GROUPMAX16)
+    if epilogue == EPI_F32_GROUPMAX16:       # out [M, N/16] fp32 group maxima, out2 [M, N/16] uint8 arg-max
+        assert N % 16 == 0
+        if out is None:
+            out = torch.empty(M, N // 16, device=a.device, dtype=torch.float32)
+        if out2 is None:
+            out2 = torch.empty(M, N // 16, device=a.device, dtype=torch.uint8)
+        assert out2.dtype == torch.uint8 and out.shape == (M, N // 16) and out2.shape == (M, N // 16)
     if out is None:
         if epilogue == EPI_F32_ATOMIC:
             out = torch.zeros(M, N, device=a.device, dtype=torch.float32)
@@ -76,7 +83,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, epilogue=EPI_BF16, alpha=1
         assert alpha_dev.dtype == torch.float32 and alpha_dev.is_cuda
         args.alpha_dev = alpha_dev.data_ptr()
     _lib.check(lib.dc_gemm_bf16(ctypes.byref(args), _stream()), "dc_gemm_bf16")
-    if epilogue == EPI_BF16_GELU:
+    if epilogue in (EPI_BF16_GELU, EPI_F32_GROUPMAX16):
         return out, out2
     return out
 

@@ -55,7 +55,10 @@ enum {
   DC_EPI_BF16_RESID = 2, /* out(bf16)  = alpha*acc + bias + aux(bf16)                        */
   DC_EPI_BF16_DGELU = 3, /* out(bf16)  = alpha*acc * quickgelu'(aux(bf16))                   */
   DC_EPI_F32 = 4,        /* out(fp32)  = alpha*acc + bias                                   */
-  DC_EPI_F32_ATOMIC = 5  /* out(fp32) += alpha*acc   (split-K allowed; red.global.add.v4.f32) */
+  DC_EPI_F32_ATOMIC = 5, /* out(fp32) += alpha*acc   (split-K allowed; red.global.add.v4.f32) */
+  DC_EPI_F32_GROUPMAX16 = 6 /* FILIP late interaction (filip.py:93-104): out(fp32)[m, g] = max over the 16 columns of group
+                             * g of alpha*acc, out2(uint8)[m, g] = index of that maximum (first one on ties); out / out2 are
+                             * [M, N/16] with row strides ldo / ldo2 — the [M, N] score matrix never leaves TMEM */
 };
 typedef struct {
   const void* A; int lda; int a_mn_major;
@@ -214,7 +217,9 @@ int dc_add_rows(const void* src, const int* idx, void* dst, int n, int width, dc
  * d2 [batch,n2,dim] fp32 (normalised). */
 int dc_token_scores(const float* d1, const float* d2, int batch, int n1, int n2, int dim, float* score1, float* score2,
                     dc_stream_t stream);
-/* out[i,l] = mean_{j<n} max_{m<group} G[i*n+j, l*group+m]; arg[(i*n+j)*ncand + l] = argmax m   (filip.py:103-104) */
+/* out[i,l] = mean_{j<n} max_{m<group} G[i*n+j, l*group+m]; arg[(i*n+j)*ncand + l] = argmax m   (filip.py:103-104).
+ * arg may be NULL; with group = 1 this is the token mean of the [batch*n, ncand] group maxima that the GEMM epilogue
+ * DC_EPI_F32_GROUPMAX16 leaves behind (the score matrix G itself is then never materialised). */
 int dc_groupmax_mean_fwd(const float* G, int ldg, int batch, int n, int group, int ncand, float* out, int ldo,
                          unsigned char* arg, dc_stream_t stream);
 /* dG (bf16 [batch*n, ncand*group]) = one-hot(arg) * dout[i,l] / n */
