@@ -316,3 +316,23 @@ def test_fused_adamw_rewrites_registered_shadow(cuda_dev):
         w.mul_(2.0)                                                    # any other in-place update re-casts lazily
     assert not shadow_current(w)
     assert torch.equal(weight_shadow(w, pad_rows=56)[:49], w.detach().bfloat16())
+
+
+@pytest.mark.parametrize("M,groups,K", [(300, 37, 256), (128, 16, 64), (1000, 513, 256), (49 * 6, 6, 256)])
+def test_gemm_groupmax16_epilogue(cuda_dev, M, groups, K):
+    """DC_EPI_F32_GROUPMAX16 (FILIP, filip.py:93-104): max / arg-max over every 16 score columns straight out of TMEM."""
+    from declip_b200 import ops
+    torch.manual_seed(M + groups)
+    a = torch.randn(M, K, device=cuda_dev).bfloat16()
+    b = torch.randn(groups * 16, K, device=cuda_dev).bfloat16()
+    s = torch.tensor([1.7], device=cuda_dev)
+    mx, arg = ops.gemm(a, b, epilogue=ops.EPI_F32_GROUPMAX16, alpha_dev=s)
+    ref = (1.7 * a.float() @ b.float().t()).view(M, groups, 16)
+    rmx, rarg = ref.max(dim=-1)
+    assert mx.shape == (M, groups) and arg.dtype == torch.uint8
+    assert torch.allclose(mx, rmx, rtol=1e-5, atol=1e-4)
+    same = arg.long() == rarg
+    # a different index is only acceptable on an exact tie of the two candidates
+    picked = ref.gather(-1, arg.long().unsqueeze(-1)).squeeze(-1)
+    assert torch.allclose(picked[~same], rmx[~same], rtol=1e-6, atol=1e-5)
+    assert same.float().mean().item() > 0.999
