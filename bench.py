@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--config", default="clip", choices=["clip", "declip", "filip", "res50"])
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling)")
     ap.add_argument("--head", default="fused", choices=["fused", "strips"],
-                    help="clip / res50: fused = csrc/head.cu (no [b,N] strip in HBM); strips = compat path returning logits")
+                    help="clip / res50 / declip: fused = csrc/head.cu (no [b,N] strip in HBM); strips = compat path returning logits")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -286,7 +286,8 @@ def build_workload(config, dev, b, world, head="fused"):
     elif config == "declip":
         cfg = dict(type='declip_vitb32', kwargs=dict(
             image_encode=dict(embed_dim=512), text_encode=dict(embed_dim=512, **text),
-            clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=512, nn_size=65536)))
+            clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=512, nn_size=65536,
+                      fused_head=head == "fused")))
     else:
         cfg = dict(type='filip_vitb32', kwargs=dict(
             image_encode=dict(embed_dim=768), text_encode=dict(embed_dim=768, **text),
@@ -511,7 +512,7 @@ def run_native(args):
             "config": {"workload": WORKLOAD_TEXT[args.config] + ", per-GPU batch %d" % b, "name": args.config,
                        "global_batch": world * b, "seq_len": 77,
                        "image": "%dx224x224 fp32" % (6 if args.config in ("declip", "filip") else 3),
-                       "parallelism": "dp%d" % world, "head": args.head if args.config in ("clip", "res50") else "strips",
+                       "parallelism": "dp%d" % world, "head": args.head if args.config in ("clip", "res50", "declip") else "strips",
                        "optimizer": "declip_b200.optim.FusedAdamW (one multi-tensor launch, "
                        "rewrites the bf16 GEMM shadows)", "l2": "inputs+activations >> 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

@@ -866,6 +866,102 @@ class FusedClipHead(torch.autograd.Function):
         return d_img, d_txt, ws[L.out + 10:L.out + 11], None, None
 
 
+class FusedPairHeads(torch.autograd.Function):
+    """Several contrastive pairs over ONE gathered feature buffer, each through the fused head kernels — DeCLIP's four
+    symmetric image/text pairs (declip.py:271-279) and its two nearest-neighbour pairs (declip.py:281-300, both strips
+    image -> text, the bank rows carry no gradient).  feats: F raw feature tensors fp32 [b, E] (normalised inside, eps per
+    feature); pairs: tuple of (x0, y0, x1, y1, cross) feature indices — direction d scores feature x_d (local rows) against
+    feature y_d (all ranks); cross = 1 when direction 1 is the transpose of direction 0.  Returns parts [P, 2] (sum of row
+    cross-entropies per pair and direction) and the per-pair workspaces."""
+
+    @staticmethod
+    def forward(ctx, logit_scale, gather, clamp, eps, pairs, *feats):
+        lib = ops.lib_for(feats[0])
+        feats = [f.float().contiguous() for f in feats]
+        nf = len(feats)
+        b, e = feats[0].shape
+        rank, world = dist_info()
+        gather = bool(gather) and world > 1
+        n, row0 = (world * b, rank * b) if gather else (b, 0)
+        dev = feats[0].device
+        L = HeadLayout.get(lib, b, e)
+        npair = len(pairs)
+        ws = torch.empty(npair, L.total, device=dev, dtype=torch.float32)
+        allb = torch.empty(n, nf * e, device=dev, dtype=torch.bfloat16)
+        local = allb[row0:row0 + b]
+        ls = logit_scale.detach()
+        fp = (_PTR * nf)(*[f.data_ptr() for f in feats])
+        ep = (ctypes.c_float * nf)(*[float(x) for x in eps])
+        for k in range(npair):        # one prepare per pair: it also clears that pair's accumulators (normalising again is ~4 us)
+            _lib.check(lib.dc_head_prepare(fp, ep, nf, b, e, _PTR(local.data_ptr()), _PTR(ws[k].data_ptr()), _PTR(ls.data_ptr()),
+                                           100.0 if clamp else float("inf"), _stream()), "dc_head_prepare")
+        if gather:
+            dist.all_gather_into_tensor(allb, local)
+        for k, (x0, y0, x1, y1, cross) in enumerate(pairs):
+            args = head_args(b, n, e, nf * e, row0, local.data_ptr(), [allb.data_ptr()], ws[k].data_ptr(),
+                             x_off=(x0 * e, x1 * e), y_off=(y0 * e, y1 * e), cross=bool(cross))
+            _lib.check(lib.dc_head_forward(ctypes.byref(args), _stream()), "dc_head_forward")
+        ctx.save_for_backward(ws, allb, *feats)
+        ctx.meta = (b, n, e, row0, gather, world, L, nf, tuple(pairs), tuple(float(x) for x in eps))
+        parts = ws[:, L.out:L.out + 2].clone()
+        ctx.mark_non_differentiable(ws)
+        return parts, ws
+
+    @staticmethod
+    def backward(ctx, gparts, _gws):
+        ws, allb = ctx.saved_tensors[:2]
+        feats = ctx.saved_tensors[2:]
+        b, n, e, row0, gather, world, L, nf, pairs, eps = ctx.meta
+        lib = ops.lib_for(allb)
+        dev = allb.device
+        npair = len(pairs)
+        g = gparts.contiguous().float()                                   # [P, 2]
+        xw = 2 * b + 2
+        if gather:
+            ws[:, L.g:L.g + 2].copy_(g)
+            mine = ws[:, L.lse:L.lse + xw].contiguous()                  # [P, 2b+2]
+            exch_all = torch.empty(world, npair, xw, device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(exch_all.view(-1), mine.view(-1))
+            exch_all = exch_all.transpose(0, 1).contiguous()              # [P, W, 2b+2]
+        local = allb[row0:row0 + b]
+        grads = [None] * nf
+        need = ctx.needs_input_grad[5:]
+        dls = None
+        for k, (x0, y0, x1, y1, cross) in enumerate(pairs):
+            exch = exch_all[k] if gather else ws[k, L.lse:L.lse + xw]
+            outs = [torch.empty(b, e, device=dev, dtype=torch.float32) if need[x] else None for x in (x0, x1)]
+            args = head_args(b, n, e, nf * e, row0, local.data_ptr(), [allb.data_ptr()], ws[k].data_ptr(),
+                             x_off=(x0 * e, x1 * e), y_off=(y0 * e, y1 * e), cross=bool(cross))
+            xraw = (_PTR * 2)(feats[x0].data_ptr(), feats[x1].data_ptr())
+            ep = (ctypes.c_float * 2)(eps[x0], eps[x1])
+            dxo = (_PTR * 2)(outs[0].data_ptr() if outs[0] is not None else None,
+                             outs[1].data_ptr() if outs[1] is not None else None)
+            _lib.check(lib.dc_head_backward(ctypes.byref(args), _PTR(g[k].data_ptr()), _PTR(exch.data_ptr()), xraw, ep, dxo,
+                                            _stream()), "dc_head_backward")
+            for x, o in zip((x0, x1), outs):
+                if o is not None:
+                    grads[x] = o if grads[x] is None else grads[x] + o
+            d = ws[k, L.out + 10:L.out + 11]
+            dls = d if dls is None else dls + d
+        return (dls, None, None, None, None) + tuple(grads)
+
+
+def fused_pair_heads(logit_scale, gather, clamp, eps, pairs, feats):
+    """-> list of (logits_a, logits_b) HANDLE pairs, one per entry of `pairs` (see FusedPairHeads / fused_clip_head)."""
+    parts, ws = FusedPairHeads.apply(logit_scale, gather, clamp, tuple(eps), tuple(pairs), *feats)
+    b, e = feats[0].shape
+    rank, world = dist_info()
+    n = world * b if (gather and world > 1) else b
+    L = HeadLayout.get(ops.lib_for(feats[0]), b, e)
+    out = []
+    for k in range(len(pairs)):
+        info = HeadInfo(parts[k], ws[k], b, n, L)
+        la, lb = ws[k, 0:1].expand(b, n), ws[k, 1:2].expand(b, n)
+        la._dc_head = lb._dc_head = info
+        out.append((la, lb))
+    return out
+
+
 def fused_clip_head(image_features, text_features, logit_scale, gather, clamp=True):
     """-> (logits_per_image, logits_per_text) HANDLES: zero-stride [b, N] views that carry `._dc_head` (HeadInfo) for
     declip_b200.loss_functions.ClipInfoCELoss; they hold no logits (use the compat path when a caller reads them)."""

