@@ -235,7 +235,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 
 int gemm_bf16(const dc_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error("gemm: empty problem");
-  if ((a.N & 7) || (a.lda & 7) || (a.ldb & 7) || (a.ldo & 3)) return set_error("gemm: N, lda, ldb must be multiples of 8");
+  const bool gmax = a.epilogue == DC_EPI_F32_GROUPMAX16;      // scalar stores of [M, N/16] values: any row stride
+  if ((a.N & 7) || (a.lda & 7) || (a.ldb & 7) || (!gmax && (a.ldo & 3)))
+    return set_error("gemm: N, lda, ldb must be multiples of 8 (ldo of 4)");
   if (a.epilogue < 0 || a.epilogue > DC_EPI_F32_GROUPMAX16) return set_error("gemm: bad epilogue");
   if (a.epilogue == DC_EPI_F32_GROUPMAX16 && (a.out2 == nullptr || (a.N & 15)))
     return set_error("gemm: the group-max epilogue needs out2 (arg-max bytes) and N % 16 == 0");
