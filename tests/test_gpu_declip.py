@@ -147,3 +147,42 @@ def test_nt_xent_family(cuda_dev, monkeypatch):
     l3r = declip_ref.nt_xent(er, fr)
     l3r.backward()
     assert abs(l3.item() - l3r.item()) < 3e-2 and _cos(e.grad.cpu(), er.grad) > 0.99
+
+
+def test_declip_from_caption_strings_with_eda(cuda_dev):
+    """The reference's real call signature: caption STRINGS in, EDA-augmented second caption view (declip.py:203-212),
+    C++ BPE, MLM masking on the device — directly and through CaptionPipeline (worker-thread tokenisation + copy stream)."""
+    import os
+    from declip_b200.loss_functions import DeclipCriterion
+    from declip_b200.model import model_entry
+    from declip_b200.tokenizer import CaptionPipeline
+    merges = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bpe_small_merges.txt")
+    cfg = dict(type='declip_vitb32', kwargs=dict(
+        image_encode=dict(embed_dim=512, layers=1),
+        text_encode=dict(bpe_path=merges, text_encode_type='Transformer', text_model_utils=dict(random=False, freeze=False),
+                         embed_dim=512, transformer_layers=1),
+        clip=dict(use_allgather=True, text_mask_type='MLM', return_nn_bank=True, feature_dim=512, nn_size=256, fused_head=True)))
+    torch.manual_seed(0)
+    model = model_entry(cfg).to(cuda_dev).train()
+    assert model.EDA and hasattr(model, "emd")
+    B = 8
+    caps = [["a photo of the big red dog running in the park number %d" % i] for i in range(B)]
+    images = torch.randn(B, 6, 224, 224)
+    crit = DeclipCriterion()
+    out = model({"images": images.to(cuda_dev), "captions": caps}, return_dict=True)
+    loss, parts, target = crit(out)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item() and set(parts) >= {"clip", "mlm", "nn", "simsiam"}
+    assert target.shape == (B,)
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    assert len(grads) > 50 and all(torch.isfinite(g).all() for g in grads)
+    model.zero_grad(set_to_none=True)
+    n = 0
+    for batch in CaptionPipeline([{"images": images, "captions": caps}] * 3, model.encode_text.tokenizer, cuda_dev, eda=model.emd):
+        assert batch["token_ids"].is_cuda and batch["token_ids_aug"].shape == (B, 77) and batch["images"].is_cuda
+        l2, _, _ = crit(model(batch, return_dict=True))
+        l2.backward()
+        n += 1
+    torch.cuda.synchronize()
+    assert n == 3 and torch.isfinite(l2).item()
