@@ -120,6 +120,8 @@ SIGNATURES = {
     "dc_head_workspace_floats": (c_size_t, [c_int, c_int]),
     "dc_head_layout": (c_int, [c_int, c_int, c_void_p]),
     "dc_head_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "dc_head_prepare_push": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p,
+                                     c_float, c_void_p]),
     "dc_head_forward": (c_int, [ctypes.POINTER(HeadArgs), c_void_p]),
     "dc_head_backward": (c_int, [ctypes.POINTER(HeadArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dc_bpe_tokenize_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),

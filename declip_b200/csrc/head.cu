@@ -91,6 +91,9 @@ struct PrepArgs {
   int n_feats, b, e;
   bf16* out;
   float* ws;
+  bf16* push[HD_MAX_SRC];              // peers' gather buffers (symmetric memory): this rank's rows are ALSO stored there
+  int n_push;
+  long long push_row0;                 // first row of this rank inside a gather buffer
   const float* logit_scale;            // raw parameter (device) or NULL
   float scale_max;                     // clamp of exp(logit_scale) (clip.py:133-134; +inf: none) / the constant scale when NULL
   long long zero_a0, zero_a1, zero_c0, zero_c1, zero_b0, zero_b1;      // float ranges to clear (b: 16-byte aligned)
@@ -109,13 +112,19 @@ __global__ void __launch_bounds__(256) head_prep_kernel(const PrepArgs a) {
       s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     const float inv = 1.0f / (sqrtf(warp_sum(s)) + a.eps[f]);
-    bf16* o = a.out + (static_cast<size_t>(row) * a.n_feats + f) * a.e;
+    const size_t off = (static_cast<size_t>(row) * a.n_feats + f) * a.e;
+    bf16* o = a.out + off;
+    const size_t poff = (static_cast<size_t>(a.push_row0 + row) * a.n_feats + f) * a.e;
     for (int c = lane * 4; c < a.e; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
       uint2 w;
       w.x = pack_bf16x2(v.x * inv, v.y * inv);
       w.y = pack_bf16x2(v.z * inv, v.w * inv);
       *reinterpret_cast<uint2*>(o + c) = w;
+      // one-shot all-gather by peer stores over NVLink: every rank ends up with all rows in its OWN buffer, which the
+      // head kernels then read through the local L2 (pulling peer tiles instead re-reads them once per row block:
+      // measured +1.7 ms/step at 2 GPUs)
+      for (int k = 0; k < a.n_push; ++k) *reinterpret_cast<uint2*>(a.push[k] + poff + c) = w;
     }
   }
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -623,8 +632,26 @@ extern "C" int dc_head_layout(int b, int e, long long* offsets8) {
   return 0;
 }
 
+static int head_prepare_impl(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows,
+                             void* const* push, int n_push, long long push_row0, float* ws, const float* logit_scale,
+                             float scale_max, dc_stream_t stream);
+
 extern "C" int dc_head_prepare(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows,
                                float* ws, const float* logit_scale, float scale_max, dc_stream_t stream) {
+  return head_prepare_impl(feats, eps, n_feats, b, e, out_rows, nullptr, 0, 0, ws, logit_scale, scale_max, stream);
+}
+
+extern "C" int dc_head_prepare_push(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows,
+                                    void* const* peer_buffers, int n_peers, long long row0, float* ws,
+                                    const float* logit_scale, float scale_max, dc_stream_t stream) {
+  if (n_peers < 0 || n_peers > HD_MAX_SRC || (n_peers > 0 && peer_buffers == nullptr))
+    return set_error("head_prepare_push: 0..8 peer buffers");
+  return head_prepare_impl(feats, eps, n_feats, b, e, out_rows, peer_buffers, n_peers, row0, ws, logit_scale, scale_max, stream);
+}
+
+static int head_prepare_impl(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows,
+                             void* const* push, int n_push, long long push_row0, float* ws, const float* logit_scale,
+                             float scale_max, dc_stream_t stream) {
   if (feats == nullptr || eps == nullptr || out_rows == nullptr || ws == nullptr) return set_error("head_prepare: null argument");
   if (n_feats < 1 || n_feats > 8) return set_error("head_prepare: 1..8 features");
   if (e % 4 != 0) return set_error("head_prepare: feature dim must be a multiple of 4");
@@ -634,6 +661,9 @@ extern "C" int dc_head_prepare(const float* const* feats, const float* eps, int 
   a.n_feats = n_feats; a.b = b; a.e = e;
   a.out = static_cast<bf16*>(out_rows);
   a.ws = ws;
+  for (int k = 0; k < n_push; ++k) a.push[k] = static_cast<bf16*>(push[k]);
+  a.n_push = n_push;
+  a.push_row0 = push_row0;
   a.logit_scale = logit_scale;
   a.scale_max = scale_max;
   const HeadWs L(b, e);

@@ -762,27 +762,31 @@ class HeadInfo:
 
 
 class _SymmFeatures:
-    """Per-rank bf16 feature rows in SYMMETRIC memory (torch.distributed._symmetric_memory): every rank's buffer is
-    mapped into every process, so the head kernels read the peers' rows straight over NVLink through one TMA tensor map
-    per rank (dc_head_args.n_src = world) and the forward needs no all-gather collective at all — only a device-side
-    barrier after the rows are written.  Two buffers alternate: the backward of step i re-reads buffer i % 2 while no
-    rank can reach the prepare of step i + 2 (which overwrites it) before every rank has passed the barrier of step
-    i + 1, i.e. has finished enqueueing its step-i backward."""
+    """Feature exchange of the fused head through SYMMETRIC memory (torch.distributed._symmetric_memory: every rank's
+    buffer is mapped into every process) instead of an NCCL all-gather.  Two flavours:
+      push : every rank owns a full gather buffer [N, F*E]; head_prep_kernel stores its normalised rows into ALL of them
+             (a one-shot all-gather by peer stores over NVLink fused into the normalisation kernel), a device-side barrier
+             follows, and the head kernels read their own buffer through the local L2 (dc_head_args.n_src = 1);
+      pull : every rank owns only its rows [b, F*E]; the head kernels read the peers' rows through one TMA tensor map per
+             rank (n_src = world).  No traffic before the kernels, but every row block re-reads the peer tiles over NVLink
+             (peer reads bypass the local L2): measured +1.7 ms/step at 2 GPUs — kept as an option, not the default.
+    Two buffers alternate: the backward of step i re-reads buffer i % 2, and no rank can overwrite it (prepare of step
+    i + 2) before every rank has passed the barrier of step i + 1, i.e. has enqueued its step-i backward."""
 
     _cache = {}
 
-    def __init__(self, b, ld, dev):
+    def __init__(self, rows, ld, dev):
         import torch.distributed._symmetric_memory as symm_mem
-        self.bufs = [symm_mem.empty((b, ld), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.bufs = [symm_mem.empty((rows, ld), dtype=torch.bfloat16, device=dev) for _ in range(2)]
         self.hdls = [symm_mem.rendezvous(t, dist.group.WORLD) for t in self.bufs]
         self.ptrs = [[int(p) for p in h.buffer_ptrs] for h in self.hdls]
         self.i = 0
 
     @classmethod
-    def get(cls, b, ld, dev):
-        key = (b, ld, str(dev))
+    def get(cls, rows, ld, dev):
+        key = (rows, ld, str(dev))
         if key not in cls._cache:
-            cls._cache[key] = cls(b, ld, dev)
+            cls._cache[key] = cls(rows, ld, dev)
         return cls._cache[key]
 
     def next(self):
@@ -791,10 +795,15 @@ class _SymmFeatures:
         return self.bufs[k], self.hdls[k], self.ptrs[k]
 
 
-def symm_head_enabled(b):
-    """Peer-memory feature exchange for the fused head: opt-in (DECLIP_B200_SYMM_HEAD=1) — needs b % 256 == 0."""
+def symm_head_mode(b):
+    """DECLIP_B200_SYMM_HEAD = push | pull | 0 (default 0: NCCL all-gather).  pull needs b % 256 == 0."""
     import os
-    return os.environ.get("DECLIP_B200_SYMM_HEAD", "0") == "1" and b % 256 == 0
+    mode = os.environ.get("DECLIP_B200_SYMM_HEAD", "0")
+    if mode in ("1", "push"):
+        return "push"
+    if mode == "pull" and b % 256 == 0:
+        return "pull"
+    return None
 
 
 class FusedClipHead(torch.autograd.Function):
@@ -815,10 +824,16 @@ class FusedClipHead(torch.autograd.Function):
         dev = img.device
         L = HeadLayout.get(lib, b, e)
         ws = torch.empty(L.total, device=dev, dtype=torch.float32)
-        symm = gather and symm_head_enabled(b)
-        if symm:
+        symm = symm_head_mode(b) if gather else None
+        push = None
+        if symm == "pull":
             local, hdl, srcs = _SymmFeatures.get(b, 2 * e, dev).next()
             allb = local
+        elif symm == "push":
+            allb, hdl, ptrs = _SymmFeatures.get(n, 2 * e, dev).next()
+            local = allb[row0:row0 + b]
+            srcs = [allb.data_ptr()]
+            push = [p for r, p in enumerate(ptrs) if r != rank]
         else:
             allb = torch.empty(n, 2 * e, device=dev, dtype=torch.bfloat16)
             local = allb[row0:row0 + b]
@@ -828,10 +843,17 @@ class FusedClipHead(torch.autograd.Function):
             raise RuntimeError("declip_b200: logit_scale must be an fp32 CUDA parameter")
         feats = (_PTR * 2)(img.data_ptr(), txt.data_ptr())
         eps = (ctypes.c_float * 2)(0.0, 1e-10)                                         # clip.py:129-130
-        _lib.check(lib.dc_head_prepare(feats, eps, 2, b, e, _PTR(local.data_ptr()), _PTR(ws.data_ptr()), _PTR(ls.data_ptr()),
-                                       100.0 if clamp else float("inf"), _stream()), "dc_head_prepare")
-        if symm:
-            hdl.barrier(channel=0)                                                     # every rank's rows are written
+        smax = 100.0 if clamp else float("inf")
+        if push is not None:
+            peers = (_PTR * len(push))(*push)
+            _lib.check(lib.dc_head_prepare_push(feats, eps, 2, b, e, _PTR(local.data_ptr()), peers, len(push), row0,
+                                                _PTR(ws.data_ptr()), _PTR(ls.data_ptr()), smax, _stream()),
+                       "dc_head_prepare_push")
+        else:
+            _lib.check(lib.dc_head_prepare(feats, eps, 2, b, e, _PTR(local.data_ptr()), _PTR(ws.data_ptr()),
+                                           _PTR(ls.data_ptr()), smax, _stream()), "dc_head_prepare")
+        if symm is not None:
+            hdl.barrier(channel=0)                                                     # every rank's rows are in place
         elif gather:
             dist.all_gather_into_tensor(allb, local)                                  # in place: `local` is rank's slice
         args = head_args(b, n, e, 2 * e, row0, local.data_ptr(), srcs, ws.data_ptr())

@@ -292,6 +292,13 @@ int dc_head_layout(int b, int e, long long* offsets8);
  * ws[out + 8] = s, ws[out + 9] = exp(logit_scale); dc_head_backward leaves d loss / d logit_scale in ws[out + 10]. */
 int dc_head_prepare(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows, float* ws,
                     const float* logit_scale, float scale_max, dc_stream_t stream);
+/* As dc_head_prepare, and additionally stores this rank's normalised rows at rows [row0, row0 + b) of every peer's gather
+ * buffer (peer_buffers: n_peers device pointers into symmetric memory, the OTHER ranks' [n, n_feats * e] buffers; out_rows
+ * then points at row row0 of this rank's own buffer): a one-shot all-gather by peer stores over NVLink fused into the
+ * normalisation kernel.  After a device barrier every rank holds all n rows locally (dc_head_args.n_src = 1). */
+int dc_head_prepare_push(const float* const* feats, const float* eps, int n_feats, int b, int e, void* out_rows,
+                         void* const* peer_buffers, int n_peers, long long row0, float* ws, const float* logit_scale,
+                         float scale_max, dc_stream_t stream);
 int dc_head_forward(const dc_head_args* a, dc_stream_t stream);
 /* g_own[2] (device): upstream gradients of this rank's sum CE_d; exch as described above (its own rank's g slots are
  * not read: g_own is used instead, so a single-rank step needs no copy at all). */
