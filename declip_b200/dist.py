@@ -213,12 +213,19 @@ class DistModule(Module):
         self._reserve_sms(False)
         rest = [p.grad for p in self.module.parameters() if p.grad is not None and id(p) not in covered]
         if rest:
-            flat = torch.cat([g.reshape(-1).float() for g in rest])
-            dist.all_reduce(flat)
-            off = 0
-            for g in rest:
-                g.copy_(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
+            # heads outside the towers (DeCLIP projector / predictor / MLM head, FILIP mappings, logit_scale): large
+            # gradients are reduced in place (no staging copy), the many small ones travel as one flat tensor
+            big = [g for g in rest if g.numel() >= (1 << 20) and g.is_contiguous()]
+            small = [g for g in rest if not (g.numel() >= (1 << 20) and g.is_contiguous())]
+            for g in big:
+                dist.all_reduce(g)
+            if small:
+                flat = torch.cat([g.reshape(-1).float() for g in small])
+                dist.all_reduce(flat)
+                off = 0
+                for g in small:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
 
     def broadcast_params(self):
         """dist.py:85-88."""
