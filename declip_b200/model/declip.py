@@ -156,9 +156,22 @@ class DECLIP(CLIP):
         ids, ids_aug, mlm = self._text_inputs(input)
         with concurrent_towers():        # text passes on a side stream, the two-view image pass on the current one
             if self.text_mask_type is not None:
-                text_features, word_features, text_labels = self.encode_text(mlm if mlm is not None else ids,
-                                                                             mask_type=self.text_mask_type)
-                text_features_aug = self.encode_text(ids_aug)
+                # The masked caption and the EDA-view caption go through the text tower as ONE 2b-sample pass (no cross-
+                # sample coupling in a transformer: identical to the reference's two calls, declip.py:215-217, with half
+                # the launches and each weight read once); the dense word features are used for the first half only.
+                if mlm is not None:
+                    mlm_ids, text_labels = mlm
+                else:
+                    if self.text_mask_type != 'MLM':
+                        raise NotImplementedError(self.text_mask_type)
+                    from .text_utils import mask_tokens_batch
+                    mlm_ids, text_labels = mask_tokens_batch(ids)                                    # text_transformer.py:154-162
+                dev = self.encode_text.positional_embedding.device
+                both = torch.cat([mlm_ids.to(dev, non_blocking=True), ids_aug.to(dev, non_blocking=True)], dim=0)
+                feats_both, words_both = self.encode_text(both, return_dense=True)
+                B = mlm_ids.shape[0]
+                text_features, text_features_aug = feats_both[:B], feats_both[B:]
+                word_features = words_both[:B]
             else:
                 text_features = self.encode_text(ids)
                 text_features_aug = self.encode_text(ids_aug) if self.EDA else text_features.detach()
