@@ -68,28 +68,56 @@ class Conv1x1(torch.autograd.Function):
         return dx, dw
 
 
+def _igemm_conv(lib, x, w_flat, B, H, W, C, cout):
+    y = torch.empty(B * H * W, cout, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.dc_conv3x3_igemm(_p(x), _p(w_flat), _p(y), B, H, W, C, cout, _stream()), "dc_conv3x3_igemm")
+    return y
+
+
+def _conv3x3_shadows(weight):
+    """bf16 [Cout, 9*Cin] (ky, kx, c) forward operand and [Cin, 9*Cout] flipped / transposed dgrad operand of a 3x3 weight,
+    re-derived only when the fp32 master changed (version counter; FusedAdamW bumps it)."""
+    cache = getattr(weight, "_dc_conv3", None)
+    if cache is not None and cache[0] == weight._version and cache[1].device == weight.device:
+        return cache[1], cache[2]
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach()
+    wf = cast_bf16(w.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous())
+    wb = cast_bf16(w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout).contiguous())
+    weight._dc_conv3 = (weight._version, wf, wb)
+    return wf, wb
+
+
 class Conv3x3(torch.autograd.Function):
-    """3x3 / pad 1 / stride 1 convolution on NHWC: im2col (K = (ky,kx,c)) + GEMM; dgrad = GEMM + col2im, wgrad = GEMM on
-    the (recomputed) im2col matrix (modified_resnet.py:23,151-154)."""
+    """3x3 / pad 1 / stride 1 convolution on NHWC (modified_resnet.py:23,151-154).  C, Cout multiples of 64: implicit GEMM
+    (csrc/conv_igemm.cu) for the forward AND the input gradient — the activation tile of each (tap, channel block) is one
+    4-D TMA box, no [rows, 9C] matrix is written in either direction; the weight gradient still contracts over an
+    im2col matrix (recomputed).  Other channel counts (the 32-channel stem): im2col + GEMM, col2im for the dgrad."""
 
     @staticmethod
     def forward(ctx, x, weight, B, H, W):
         lib = ops.lib_for(x)
         C = x.shape[1]
         cout = weight.shape[0]
-        col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.bfloat16)
-        _lib.check(lib.dc_im2col3x3(_p(x), _p(col), B, H, W, C, _stream()), "dc_im2col3x3")
-        w16 = cast_bf16(weight.permute(0, 2, 3, 1).reshape(cout, 9 * C).contiguous())
-        y = ops.gemm(col, w16)
-        ctx.save_for_backward(x, w16)
-        ctx.geom = (B, H, W, C, cout)
+        igemm = bool(lib.dc_conv3x3_igemm_supported(H, W, C, cout)) and bool(lib.dc_conv3x3_igemm_supported(H, W, cout, C))
+        if igemm:
+            w16, wb16 = _conv3x3_shadows(weight)
+            y = _igemm_conv(lib, x.contiguous(), w16, B, H, W, C, cout)
+            ctx.save_for_backward(x, wb16)
+        else:
+            col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.bfloat16)
+            _lib.check(lib.dc_im2col3x3(_p(x), _p(col), B, H, W, C, _stream()), "dc_im2col3x3")
+            w16 = cast_bf16(weight.permute(0, 2, 3, 1).reshape(cout, 9 * C).contiguous())
+            y = ops.gemm(col, w16)
+            ctx.save_for_backward(x, w16)
+        ctx.geom = (B, H, W, C, cout, igemm)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w16 = ctx.saved_tensors
+        x, wsaved = ctx.saved_tensors
         lib = ops.lib_for(x)
-        B, H, W, C, cout = ctx.geom
+        B, H, W, C, cout, igemm = ctx.geom
         dy = dy.contiguous()
         col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.bfloat16)
         _lib.check(lib.dc_im2col3x3(_p(x), _p(col), B, H, W, C, _stream()), "dc_im2col3x3")
@@ -97,9 +125,12 @@ class Conv3x3(torch.autograd.Function):
         dw = dw.reshape(cout, 3, 3, C).permute(0, 3, 1, 2).contiguous()
         dx = None
         if ctx.needs_input_grad[0]:
-            dcol = ops.gemm(dy, w16, b_mn_major=True)                                               # [rows, 9C] (reuses col's size)
-            dx = torch.empty_like(x)
-            _lib.check(lib.dc_col2im3x3(_p(dcol), _p(dx), B, H, W, C, _stream()), "dc_col2im3x3")
+            if igemm:      # dx = conv3x3(dy, flipped / transposed weights): the same kernel, no dcol / col2im
+                dx = _igemm_conv(lib, dy, wsaved, B, H, W, cout, C)
+            else:
+                dcol = ops.gemm(dy, wsaved, b_mn_major=True)                                        # [rows, 9C]
+                dx = torch.empty_like(x)
+                _lib.check(lib.dc_col2im3x3(_p(dcol), _p(dx), B, H, W, C, _stream()), "dc_col2im3x3")
         return dx, dw, None, None, None
 
 

@@ -252,6 +252,14 @@ int dc_add_bf16(const void* a, const void* b, void* out, size_t n, dc_stream_t s
 int dc_attnpool_assemble(const void* x, const float* pos, void* tokens, int batch, int P, int C, dc_stream_t stream);
 int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, int C, dc_stream_t stream);
 
+/* ------------------------------------------------------------------ implicit-GEMM 3x3 convolution (conv_igemm.cu)
+ * out[B*H*W, Cout] (bf16, NHWC) = conv3x3(x[B*H*W, C] NHWC bf16, pad 1, stride 1) with w [Cout, 9*C] bf16 ordered
+ * (ky, kx, c) — modified_resnet.py:23,151-154.  The A operand of every k-block is a 4-D TMA box of x shifted by the tap
+ * offset (out-of-bounds zero fill = padding): no im2col matrix.  The input gradient is the same call on dy with
+ * w' [C, 9*Cout], w'[ci, (ky, kx, co)] = w[co, (2-ky, 2-kx, ci)].  Needs C % 64 == 0, Cout % 64 == 0, W <= 128. */
+int dc_conv3x3_igemm_supported(int H, int W, int C, int Cout);
+int dc_conv3x3_igemm(const void* x, const void* w, void* out, int batch, int H, int W, int C, int Cout, dc_stream_t stream);
+
 /* ------------------------------------------------------------------ fused distributed contrastive head (head.cu)
  * Replaces, for a symmetric image/text pair, the whole chain clip.py:129-146 (normalise, AllGather, two logit
  * strips) + loss_functions/loss.py:40-50 (ClipInfoCELoss) + utils/misc.py:415-428 (accuracy) and its autograd backward

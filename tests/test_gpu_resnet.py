@@ -224,3 +224,25 @@ def test_bottleneck_block_isolated(cuda_dev, inplanes, planes, stride, H):
     assert _cos(_nchw(xh.grad, B, H, H), xr.grad) > 0.99
     for k, gref in P.items():
         assert _cos(mine[k], gref.grad) > 0.98, (k, _cos(mine[k], gref.grad))
+
+
+@pytest.mark.parametrize("B,C,Cout,H", [(3, 64, 64, 56), (2, 128, 128, 28), (5, 256, 256, 14), (5, 512, 512, 7), (3, 64, 128, 56),
+                                        (1, 128, 64, 28), (7, 512, 512, 7)])
+def test_conv3x3_implicit_gemm(cuda_dev, B, C, Cout, H):
+    """csrc/conv_igemm.cu: forward and input gradient through 4-D TMA boxes (padding = out-of-bounds zero fill), weight
+    gradient through the im2col GEMM — against torch conv2d in fp32 on the same bf16-rounded operands."""
+    from declip_b200 import functions_conv as C_
+    torch.manual_seed(B * 1000 + C + H)
+    x = torch.randn(B, C, H, H, device=cuda_dev)
+    xh = _nhwc(x).requires_grad_(True)
+    xr = xh.detach().float().view(B, H, H, C).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    w = (torch.randn(Cout, C, 3, 3, device=cuda_dev) * (9 * C) ** -0.5).requires_grad_(True)
+    y = C_.Conv3x3.apply(xh, w, B, H, H)
+    wr = w.detach().bfloat16().float().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+    assert _rel(_nchw(y, B, H, H), yr) < 5e-3
+    g = torch.randn_like(yr)
+    y.backward(_nhwc(g))
+    yr.backward(_nhwc(g).float().view(B, H, H, Cout).permute(0, 3, 1, 2))
+    assert _rel(_nchw(xh.grad, B, H, H), xr.grad) < 6e-3
+    assert _cos(w.grad, wr.grad) > 0.9995
