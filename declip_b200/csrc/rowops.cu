@@ -188,6 +188,111 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ dy
   }
 }
 
+// Round-2 variant: a GROUP of NV warps per row, ONE 16-byte vector per lane and tensor.  The one-warp-per-row kernel above
+// needs 188-253 registers per thread (72-96 fp32 column accumulators per lane) and so runs 8 warps per SM: ncu shows the
+// issue slots 33 % busy and 12 % of the warp slots occupied — latency-bound at 0.56 of the HBM floor.  Here every lane
+// owns 8 columns (24 accumulators, ~60 registers), 24 warps fit an SM, and the two row statistics are combined across the
+// NV warps of a group through shared memory with one named barrier per row (double-buffered slots).
+template <int NV>
+__global__ void __launch_bounds__(NV * 32 * (24 / NV)) ln_bwd_group_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ dcol, int rows) {
+  constexpr int W = NV * 256;
+  constexpr int GROUPS = 24 / NV;                 // row groups per block (24 warps)
+  __shared__ float s_acc[3 * W];
+  __shared__ float s_part[2][GROUPS][NV][2];
+  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int grp = warp / NV, wig = warp - grp * NV;            // group inside the block, warp inside the group
+  const int col = (wig * 32 + lane) * 8;
+  const int row_stride = gridDim.x * GROUPS;
+  float g[8], ag[8], ab[8], ao[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; ao[i] = 0.f; }
+  }
+  int row = blockIdx.x * GROUPS + grp;
+  uint4 cx = make_uint4(0u, 0u, 0u, 0u), cdy = cx, cdr = cx;
+  if (row < rows) {
+    const size_t base = static_cast<size_t>(row) * W + col;
+    cx = *reinterpret_cast<const uint4*>(x + base);
+    cdy = *reinterpret_cast<const uint4*>(dy + base);
+    if (dres != nullptr) cdr = *reinterpret_cast<const uint4*>(dres + base);
+  }
+  int it = 0;
+  for (; row < rows; row += row_stride, ++it) {
+    const int nrow = row + row_stride;
+    uint4 nx = make_uint4(0u, 0u, 0u, 0u), ndy = nx, ndr = nx;
+    if (nrow < rows) {                     // next row in flight while this one is reduced
+      const size_t nb = static_cast<size_t>(nrow) * W + col;
+      nx = *reinterpret_cast<const uint4*>(x + nb);
+      ndy = *reinterpret_cast<const uint4*>(dy + nb);
+      if (dres != nullptr) ndr = *reinterpret_cast<const uint4*>(dres + nb);
+    }
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float xv[8], dv[8], xh[8];
+    unpack8(cx, xv);
+    unpack8(cdy, dv);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[i] = (xv[i] - mu) * rs;
+      const float gy = dv[i] * g[i];
+      s1 += gy;
+      s2 = fmaf(gy, xh[i], s2);
+      ag[i] = fmaf(dv[i], xh[i], ag[i]);
+      ab[i] += dv[i];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (NV > 1) {
+      float* slot = &s_part[it & 1][grp][0][0];
+      if (lane == 0) { slot[wig * 2] = s1; slot[wig * 2 + 1] = s2; }
+      asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NV * 32) : "memory");
+      s1 = 0.f; s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) { s1 += slot[k * 2]; s2 += slot[k * 2 + 1]; }
+    }
+    const float c1 = s1 * (1.0f / W), c2 = s2 * (1.0f / W);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rs * (dv[i] * g[i] - c1 - xh[i] * c2);
+    if (dres != nullptr) {
+      float rv[8];
+      unpack8(cdr, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += rv[i];
+    }
+    if (dcol != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ao[i] += o[i];
+    }
+    uint4 w;
+    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * W + col) = w;
+    cx = nx; cdy = ndy; cdr = ndr;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&s_acc[col + i], ag[i]);
+    atomicAdd(&s_acc[W + col + i], ab[i]);
+    if (dcol != nullptr) atomicAdd(&s_acc[2 * W + col + i], ao[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_acc[i]);
+    atomicAdd(&dbeta[i], s_acc[W + i]);
+    if (dcol != nullptr) atomicAdd(&dcol[i], s_acc[2 * W + i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Column sums (bias gradients): out[c] += sum_r x[r,c].  Block = 8 column-vectors x 32 row lanes,
 // 64 columns x ROWS_PER_BLOCK rows per block; warp loads are 4 rows x 128 contiguous bytes.
@@ -630,12 +735,29 @@ int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
                      dc_stream_t stream) {
   if (rows <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // one resident block per SM (188-253 registers/thread): more blocks only multiply the per-block atomics epilogue
-  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 1);
   const bf16* dyp = static_cast<const bf16*>(dy);
   const bf16* xp = static_cast<const bf16*>(x);
   const bf16* rp = static_cast<const bf16*>(dres);
   bf16* dxp = static_cast<bf16*>(dx);
+  static const bool v1 = [] { const char* e = getenv("DC_LN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
+  if (!v1 && (width == 256 || width == 512 || width == 768 || width == 1024)) {
+    // warp-group-per-row kernel: one 768-thread block per SM (24 warps), blocks walk the rows with stride grid x groups
+    const int nv = width / 256;
+    const int groups = 24 / nv;
+    int grid = (rows + groups - 1) / groups;
+    if (grid > sm_count()) grid = sm_count();
+    const int threads = nv * 32 * groups;
+    switch (nv) {
+      case 1: ln_bwd_group_kernel<1><<<grid, threads, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+      case 2: ln_bwd_group_kernel<2><<<grid, threads, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+      case 3: ln_bwd_group_kernel<3><<<grid, threads, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+      default: ln_bwd_group_kernel<4><<<grid, threads, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
+    }
+    DC_CHECK_LAUNCH("layernorm_bwd");
+    return 0;
+  }
+  // round-1 kernel: one resident block per SM (188-253 registers/thread)
+  const int grid = grid_for(static_cast<size_t>(rows) * 32, 256, 1);
   switch (width) {
     case 256: ln_bwd_kernel<1><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
     case 512: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows); break;
