@@ -58,39 +58,61 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ 3x3, pad 1, stride 1
-// col[(b,y,x), (ky*3+kx)*C + c] = in[(b, y-1+ky, x-1+kx), c]  (zero outside).  One 16-byte vector per thread-iteration.
+// col[(b,y,x), (ky*3+kx)*C + c] = in[(b, y-1+ky, x-1+kx), c]  (zero outside).  One block walks image rows (b, y); a
+// thread owns ONE (tap, 8-channel vector) slot of the 9 * C / 8 slots of a pixel and steps over x, so the inner loop has no
+// integer division (the first version did five 64-bit divisions per 16 bytes and ran at 2 TB/s) and a warp writes one
+// contiguous run of the column matrix.  Launch with blockDim.x a multiple of 9 * C / 8 (or 256 when that exceeds 256).
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ col, int batch,
                                                         int H, int W, int C) {
-  const int vc = C / 8;
-  const size_t total = static_cast<size_t>(batch) * H * W * 9 * vc;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int c = static_cast<int>(t % vc) * 8;
-    size_t q = t / vc;
-    const int tap = static_cast<int>(q % 9);
-    q /= 9;
-    const int x = static_cast<int>(q % W);
-    const int y = static_cast<int>((q / W) % H);
-    const size_t b = q / (static_cast<size_t>(W) * H);
-    const int iy = y - 1 + tap / 3, ix = x - 1 + tap % 3;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-      v = *reinterpret_cast<const uint4*>(in + ((b * H + iy) * W + ix) * C + c);
-    *reinterpret_cast<uint4*>(col + q * (9 * static_cast<size_t>(C)) + static_cast<size_t>(tap) * C + c) = v;
+  const int vc = C / 8, R = 9 * vc;
+  const int nrows = batch * H;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  if (blockDim.x % R == 0) {
+    const int px = blockDim.x / R;                      // pixels per pass
+    const int x0 = threadIdx.x / R, r = threadIdx.x - x0 * R;
+    const int tap = r / vc, c = (r - tap * vc) * 8;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+      const int b = row / H, y = row - b * H;
+      const int iy = y - 1 + ky;
+      const bool yok = iy >= 0 && iy < H;
+      const bf16* src = in + (static_cast<size_t>(b) * H + (yok ? iy : 0)) * W * C + c;
+      bf16* dst = col + static_cast<size_t>(row) * W * (9 * static_cast<size_t>(C)) + static_cast<size_t>(r) * 8;
+#pragma unroll 4
+      for (int x = x0; x < W; x += px) {
+        const int ix = x - 1 + kx;
+        uint4 v = zero;
+        if (yok && ix >= 0 && ix < W) v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(ix) * C);
+        *reinterpret_cast<uint4*>(dst + static_cast<size_t>(x) * (9 * static_cast<size_t>(C))) = v;
+      }
+    }
+    return;
+  }
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int b = row / H, y = row - b * H;
+    bf16* dst = col + static_cast<size_t>(row) * W * (9 * static_cast<size_t>(C));
+    for (int idx = threadIdx.x; idx < W * R; idx += blockDim.x) {
+      const int x = idx / R, r = idx - x * R;
+      const int tap = r / vc, c = (r - tap * vc) * 8;
+      const int iy = y - 1 + tap / 3, ix = x - 1 + tap % 3;
+      uint4 v = zero;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + iy) * W + ix) * C + c);
+      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(idx) * 8) = v;
+    }
   }
 }
 // dgrad of the above: din[(b,y,x), c] = sum over taps of dcol[(b, y+1-ky, x+1-kx), tap*C + c]  (a gather: no atomics)
 __global__ void __launch_bounds__(256) col2im3x3_kernel(const bf16* __restrict__ dcol, bf16* __restrict__ din, int batch,
                                                         int H, int W, int C) {
   const int vc = C / 8;
-  const size_t total = static_cast<size_t>(batch) * H * W * vc;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int c = static_cast<int>(t % vc) * 8;
-    const size_t q = t / vc;
-    const int x = static_cast<int>(q % W);
-    const int y = static_cast<int>((q / W) % H);
-    const size_t b = q / (static_cast<size_t>(W) * H);
+  const int nrows = batch * H;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x)
+  for (int idx = threadIdx.x; idx < W * vc; idx += blockDim.x) {
+    const int x = idx / vc, c = (idx - x * vc) * 8;
+    const size_t b = static_cast<size_t>(row / H);
+    const int y = row - static_cast<int>(b) * H;
+    const size_t q = static_cast<size_t>(row) * W + x;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
@@ -116,14 +138,13 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) avgpool2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int batch,
                                                        int H, int W, int C, int backward) {
   const int OH = H / 2, OW = W / 2, vc = C / 8;
-  const size_t total = static_cast<size_t>(batch) * OH * OW * vc;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int c = static_cast<int>(t % vc) * 8;
-    const size_t q = t / vc;
-    const int ox = static_cast<int>(q % OW);
-    const int oy = static_cast<int>((q / OW) % OH);
-    const size_t b = q / (static_cast<size_t>(OW) * OH);
+  const int nrows = batch * OH;                       // block-per-output-row walk: 32-bit index math only
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x)
+  for (int idx = threadIdx.x; idx < OW * vc; idx += blockDim.x) {
+    const int ox = idx / vc, c = (idx - ox * vc) * 8;
+    const size_t b = static_cast<size_t>(row / OH);
+    const int oy = row - static_cast<int>(b) * OH;
+    const size_t q = static_cast<size_t>(row) * OW + ox;
     const size_t i00 = ((b * H + 2 * oy) * W + 2 * ox) * C + c;
     const size_t offs[4] = {i00, i00 + C, i00 + static_cast<size_t>(W) * C, i00 + static_cast<size_t>(W) * C + C};
     if (!backward) {
@@ -233,74 +254,139 @@ __global__ void bn2d_eval_stats_kernel(const float* __restrict__ run_mean, const
 }
 
 // y = [relu]( (x - mean) * rstd * gamma + beta [+ res] )
-__global__ void __launch_bounds__(256) bn2d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
-                                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, const bf16* __restrict__ res,
-                                                         bf16* __restrict__ y, size_t rows, int C, int relu) {
-  const int vc = C / 8;
-  const size_t total = rows * vc;
+// The grid stride is a multiple of C / 8 (the host rounds the grid), so a thread owns ONE group of 8 channels for its
+// whole loop: the per-channel scale / shift live in registers and the loop body is loads, 8 FMAs and a store — no
+// per-element integer division, no per-element parameter loads (the first version spent its time on both: 1.6 TB/s).
+// UNR independent 16-byte loads per operand are issued before the first use to cover the HBM latency.
+template <bool RES, bool RELU>
+__global__ void __launch_bounds__(256, 4) bn2d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const bf16* __restrict__ res,
+                                                            bf16* __restrict__ y, size_t total, int vc) {
+  constexpr int UNR = RES ? 2 : 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int c = static_cast<int>(t % vc) * 8;
-    float xv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + t * 8), xv);
+  const size_t t0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int c = static_cast<int>(t0 % static_cast<size_t>(vc)) * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = (xv[i] - mean[c + i]) * rstd[c + i] * gamma[c + i] + beta[c + i];
-    if (res != nullptr) {
-      float rv[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + t * 8), rv);
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = rstd[c + i] * gamma[c + i];
+    sh[i] = beta[c + i] - mean[c + i] * sc[i];
+  }
+  const uint4* xv = reinterpret_cast<const uint4*>(x);
+  const uint4* rv = reinterpret_cast<const uint4*>(res);
+  uint4* yv = reinterpret_cast<uint4*>(y);
+  for (size_t t = t0; t < total; t += stride * UNR) {
+    uint4 xin[UNR], rin[UNR];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += rv[i];
+    for (int u = 0; u < UNR; ++u) {
+      const size_t tt = t + u * stride;
+      if (tt < total) {
+        xin[u] = xv[tt];
+        if (RES) rin[u] = rv[tt];
+      }
     }
-    if (relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+    for (int u = 0; u < UNR; ++u) {
+      const size_t tt = t + u * stride;
+      if (tt >= total) break;
+      float f[8], o[8];
+      unpack8(xin[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(f[i], sc[i], sh[i]);
+      if (RES) {
+        unpack8(rin[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += f[i];
+      }
+      if (RELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      yv[tt] = w;
     }
-    uint4 w;
-    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(y + t * 8) = w;
   }
 }
 
-// dx = gamma * rstd * (g - m1 - xhat * m2), g = dy * relu-mask; optionally dres = g (gradient of the residual input)
-__global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                             const bf16* __restrict__ y, const float* __restrict__ mean,
-                                                             const float* __restrict__ rstd,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ sums, bf16* __restrict__ dx,
-                                                             bf16* __restrict__ dres, size_t rows, int C, int relu) {
-  const int vc = C / 8;
-  const size_t total = rows * vc;
+// dx = gamma * rstd * (g - m1 - xhat * m2), g = dy * relu-mask; optionally dres = g (gradient of the residual input).
+// Same thread <-> channel-group ownership as the forward: dx = ka * g + kb * x + kc with per-channel constants in registers.
+template <bool RELU, bool DRES>
+__global__ void __launch_bounds__(256, 3) bn2d_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                const bf16* __restrict__ y, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd,
+                                                                const float* __restrict__ gamma,
+                                                                const float* __restrict__ sums, bf16* __restrict__ dx,
+                                                                bf16* __restrict__ dres, size_t total, int vc, float invr) {
+  constexpr int UNR = 2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  const float invr = 1.0f / static_cast<float>(rows);
-  for (size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const int c = static_cast<int>(t % vc) * 8;
-    float gv[8], xv[8], yv[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + t * 8), gv);
-    unpack8(*reinterpret_cast<const uint4*>(x + t * 8), xv);
-    if (relu) {
-      unpack8(*reinterpret_cast<const uint4*>(y + t * 8), yv);
+  const size_t t0 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int C = vc * 8;
+  const int c = static_cast<int>(t0 % static_cast<size_t>(vc)) * 8;
+  float ka[8], kb[8], kc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (yv[i] <= 0.f) gv[i] = 0.f;
+  for (int i = 0; i < 8; ++i) {
+    const float rs = rstd[c + i], m1 = sums[c + i] * invr, m2 = sums[C + c + i] * invr;
+    ka[i] = gamma[c + i] * rs;
+    kb[i] = -ka[i] * rs * m2;
+    kc[i] = -ka[i] * m1 - kb[i] * mean[c + i];
+  }
+  const uint4* gv4 = reinterpret_cast<const uint4*>(dy);
+  const uint4* xv4 = reinterpret_cast<const uint4*>(x);
+  const uint4* yv4 = reinterpret_cast<const uint4*>(y);
+  uint4* dxv = reinterpret_cast<uint4*>(dx);
+  uint4* drv = reinterpret_cast<uint4*>(dres);
+  for (size_t t = t0; t < total; t += stride * UNR) {
+    uint4 gin[UNR], xin[UNR], yin[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const size_t tt = t + u * stride;
+      if (tt < total) {
+        gin[u] = gv4[tt];
+        xin[u] = xv4[tt];
+        if (RELU) yin[u] = yv4[tt];
+      }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xh = (xv[i] - mean[c + i]) * rstd[c + i];
-      o[i] = gamma[c + i] * rstd[c + i] * (gv[i] - sums[c + i] * invr - xh * sums[C + c + i] * invr);
-    }
-    uint4 w;
-    w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-    w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(dx + t * 8) = w;
-    if (dres != nullptr) {
-      uint4 g;
-      g.x = pack_bf16x2(gv[0], gv[1]); g.y = pack_bf16x2(gv[2], gv[3]);
-      g.z = pack_bf16x2(gv[4], gv[5]); g.w = pack_bf16x2(gv[6], gv[7]);
-      *reinterpret_cast<uint4*>(dres + t * 8) = g;
+    for (int u = 0; u < UNR; ++u) {
+      const size_t tt = t + u * stride;
+      if (tt >= total) break;
+      float gv[8], xv[8], o[8];
+      unpack8(gin[u], gv);
+      unpack8(xin[u], xv);
+      if (RELU) {
+        float yv[8];
+        unpack8(yin[u], yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (yv[i] <= 0.f) gv[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(ka[i], gv[i], fmaf(kb[i], xv[i], kc[i]));
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      dxv[tt] = w;
+      if (DRES) {
+        uint4 g;
+        g.x = pack_bf16x2(gv[0], gv[1]); g.y = pack_bf16x2(gv[2], gv[3]);
+        g.z = pack_bf16x2(gv[4], gv[5]); g.w = pack_bf16x2(gv[6], gv[7]);
+        drv[tt] = g;
+      }
     }
   }
+}
+
+// grid for the channel-owning elementwise kernels: blocks * 256 must be a multiple of vc = C / 8
+static inline int bn_apply_grid(size_t total, int vc, int per_sm) {
+  int g = grid_for_items(total, 256, per_sm);
+  int a = vc, b = 256;
+  while (b) { const int r = a % b; a = b; b = r; }      // a = gcd(vc, 256)
+  const int q = vc / a;                                  // the grid must be a multiple of q
+  g = (g + q - 1) / q * q;
+  return g;
 }
 
 __global__ void bn2d_acc_kernel(const float* __restrict__ s, float* __restrict__ dg, float* __restrict__ db, int C) {
@@ -394,8 +480,12 @@ int dc_im2col_stem(const float* images, long long sample_stride, void* col, int 
 
 int dc_im2col3x3(const void* in, void* col, int batch, int H, int W, int C, dc_stream_t stream) {
   if (C & 7) return set_error("im2col3x3: C must be a multiple of 8");
-  const size_t total = static_cast<size_t>(batch) * H * W * 9 * (C / 8);
-  im2col3x3_kernel<<<grid_for_items(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (static_cast<long long>(batch) * H >= (1ll << 31)) return set_error("im2col3x3: batch * H must fit 31 bits");
+  const int R = 9 * (C / 8);
+  const int threads = R <= 256 ? (256 / R) * R : 256;
+  int blocks = batch * H;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  im2col3x3_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(in), static_cast<bf16*>(col), batch, H, W, C);
   DC_CHECK_LAUNCH("im2col3x3");
   return 0;
@@ -403,8 +493,10 @@ int dc_im2col3x3(const void* in, void* col, int batch, int H, int W, int C, dc_s
 
 int dc_col2im3x3(const void* dcol, void* din, int batch, int H, int W, int C, dc_stream_t stream) {
   if (C & 7) return set_error("col2im3x3: C must be a multiple of 8");
-  const size_t total = static_cast<size_t>(batch) * H * W * (C / 8);
-  col2im3x3_kernel<<<grid_for_items(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (static_cast<long long>(batch) * H >= (1ll << 31)) return set_error("col2im3x3: batch * H must fit 31 bits");
+  int blocks = batch * H;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  col2im3x3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(dcol), static_cast<bf16*>(din), batch, H, W, C);
   DC_CHECK_LAUNCH("col2im3x3");
   return 0;
@@ -412,8 +504,9 @@ int dc_col2im3x3(const void* dcol, void* din, int batch, int H, int W, int C, dc
 
 int dc_avgpool2(const void* in, void* out, int batch, int H, int W, int C, int backward, dc_stream_t stream) {
   if ((C & 7) || ((H | W) & 1)) return set_error("avgpool2: C % 8 == 0 and even H, W required");
-  const size_t total = static_cast<size_t>(batch) * (H / 2) * (W / 2) * (C / 8);
-  avgpool2_kernel<<<grid_for_items(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  int blocks = batch * (H / 2);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  avgpool2_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(in), static_cast<bf16*>(out), batch, H, W, C, backward);
   DC_CHECK_LAUNCH("avgpool2");
   return 0;
@@ -440,9 +533,17 @@ int dc_bn2d_fwd(const void* x, const float* gamma, const float* beta, const void
     bn2d_eval_stats_kernel<<<(C + 255) / 256, 256, 0, st>>>(running_mean, running_var, mean, rstd, C, eps);
     DC_CHECK_LAUNCH("bn2d_eval_stats");
   }
-  bn2d_apply_kernel<<<grid_for_items(static_cast<size_t>(rows) * (C / 8), 256), 256, 0, st>>>(
-      static_cast<const bf16*>(x), mean, rstd, gamma, beta, static_cast<const bf16*>(res), static_cast<bf16*>(y),
-      static_cast<size_t>(rows), C, relu);
+  {
+    const size_t total = static_cast<size_t>(rows) * (C / 8);
+    const int g = bn_apply_grid(total, C / 8, 4);
+    const bf16* xp = static_cast<const bf16*>(x);
+    const bf16* rp = static_cast<const bf16*>(res);
+    bf16* yp = static_cast<bf16*>(y);
+    if (res != nullptr && relu) bn2d_apply_kernel<true, true><<<g, 256, 0, st>>>(xp, mean, rstd, gamma, beta, rp, yp, total, C / 8);
+    else if (res != nullptr) bn2d_apply_kernel<true, false><<<g, 256, 0, st>>>(xp, mean, rstd, gamma, beta, rp, yp, total, C / 8);
+    else if (relu) bn2d_apply_kernel<false, true><<<g, 256, 0, st>>>(xp, mean, rstd, gamma, beta, rp, yp, total, C / 8);
+    else bn2d_apply_kernel<false, false><<<g, 256, 0, st>>>(xp, mean, rstd, gamma, beta, rp, yp, total, C / 8);
+  }
   DC_CHECK_LAUNCH("bn2d_apply");
   return 0;
 }
@@ -459,9 +560,21 @@ int dc_bn2d_bwd(const void* dy, const void* x, const void* y, const float* gamma
                                           static_cast<const bf16*>(y), mean, rstd, scratch, static_cast<size_t>(rows), C, 1,
                                           relu);
   DC_CHECK_LAUNCH("bn2d_bwd_stats");
-  bn2d_bwd_apply_kernel<<<grid_for_items(static_cast<size_t>(rows) * (C / 8), 256), 256, 0, st>>>(
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(y), mean, rstd, gamma, scratch,
-      static_cast<bf16*>(dx), static_cast<bf16*>(dres), static_cast<size_t>(rows), C, relu);
+  {
+    const size_t total = static_cast<size_t>(rows) * (C / 8);
+    const int g = bn_apply_grid(total, C / 8, 3);
+    const float invr = 1.0f / static_cast<float>(rows);
+    const bf16 *gp = static_cast<const bf16*>(dy), *xp = static_cast<const bf16*>(x), *yp = static_cast<const bf16*>(y);
+    bf16 *dxp = static_cast<bf16*>(dx), *drp = static_cast<bf16*>(dres);
+    if (relu && dres != nullptr)
+      bn2d_bwd_apply_kernel<true, true><<<g, 256, 0, st>>>(gp, xp, yp, mean, rstd, gamma, scratch, dxp, drp, total, C / 8, invr);
+    else if (relu)
+      bn2d_bwd_apply_kernel<true, false><<<g, 256, 0, st>>>(gp, xp, yp, mean, rstd, gamma, scratch, dxp, drp, total, C / 8, invr);
+    else if (dres != nullptr)
+      bn2d_bwd_apply_kernel<false, true><<<g, 256, 0, st>>>(gp, xp, yp, mean, rstd, gamma, scratch, dxp, drp, total, C / 8, invr);
+    else
+      bn2d_bwd_apply_kernel<false, false><<<g, 256, 0, st>>>(gp, xp, yp, mean, rstd, gamma, scratch, dxp, drp, total, C / 8, invr);
+  }
   DC_CHECK_LAUNCH("bn2d_bwd_apply");
   // dbeta = sum g, dgamma = sum g * xhat  (scratch) -> accumulate
   if (dgamma != nullptr || dbeta != nullptr) {

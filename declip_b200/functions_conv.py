@@ -2,6 +2,8 @@
 C ABI.  Activations are NHWC bf16 matrices [B*H*W, C]; convolutions are (im2col +) the tcgen05 GEMM."""
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -119,9 +121,14 @@ class Conv3x3(torch.autograd.Function):
         lib = ops.lib_for(x)
         B, H, W, C, cout, igemm = ctx.geom
         dy = dy.contiguous()
-        col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.bfloat16)
-        _lib.check(lib.dc_im2col3x3(_p(x), _p(col), B, H, W, C, _stream()), "dc_im2col3x3")
-        dw = ops.gemm(dy, col, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)     # [cout, 9C]
+        if igemm and W <= 64 and os.environ.get("DECLIP_B200_CONV_WGRAD", "igemm") == "igemm":
+            # contraction over spatial TMA boxes of dy and (shifted) x: no im2col matrix for the weight gradient either
+            dw = torch.zeros(cout, 9 * C, device=x.device, dtype=torch.float32)
+            _lib.check(lib.dc_conv3x3_wgrad_igemm(_p(dy), _p(x), _p(dw), B, H, W, C, cout, _stream()), "dc_conv3x3_wgrad_igemm")
+        else:
+            col = torch.empty(B * H * W, 9 * C, device=x.device, dtype=torch.bfloat16)
+            _lib.check(lib.dc_im2col3x3(_p(x), _p(col), B, H, W, C, _stream()), "dc_im2col3x3")
+            dw = ops.gemm(dy, col, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC)     # [cout, 9C]
         dw = dw.reshape(cout, 3, 3, C).permute(0, 3, 1, 2).contiguous()
         dx = None
         if ctx.needs_input_grad[0]:

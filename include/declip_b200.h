@@ -259,6 +259,10 @@ int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, in
  * w' [C, 9*Cout], w'[ci, (ky, kx, co)] = w[co, (2-ky, 2-kx, ci)].  Needs C % 64 == 0, Cout % 64 == 0, W <= 128. */
 int dc_conv3x3_igemm_supported(int H, int W, int C, int Cout);
 int dc_conv3x3_igemm(const void* x, const void* w, void* out, int batch, int H, int W, int C, int Cout, dc_stream_t stream);
+/* dw[Cout, 9*C] (fp32, (ky, kx, c) order) += sum over pixels of dy[p, co] * x[p + tap offset, ci]: the contraction runs over
+ * spatial TMA boxes of both NHWC tensors (MN-major operands), split over CTAs with fp32 atomics.  W <= 64. */
+int dc_conv3x3_wgrad_igemm(const void* dy, const void* x, float* dw, int batch, int H, int W, int C, int Cout,
+                           dc_stream_t stream);
 
 /* ------------------------------------------------------------------ fused distributed contrastive head (head.cu)
  * Replaces, for a symmetric image/text pair, the whole chain clip.py:129-146 (normalise, AllGather, two logit

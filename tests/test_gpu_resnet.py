@@ -229,8 +229,8 @@ def test_bottleneck_block_isolated(cuda_dev, inplanes, planes, stride, H):
 @pytest.mark.parametrize("B,C,Cout,H", [(3, 64, 64, 56), (2, 128, 128, 28), (5, 256, 256, 14), (5, 512, 512, 7), (3, 64, 128, 56),
                                         (1, 128, 64, 28), (7, 512, 512, 7)])
 def test_conv3x3_implicit_gemm(cuda_dev, B, C, Cout, H):
-    """csrc/conv_igemm.cu: forward and input gradient through 4-D TMA boxes (padding = out-of-bounds zero fill), weight
-    gradient through the im2col GEMM — against torch conv2d in fp32 on the same bf16-rounded operands."""
+    """csrc/conv_igemm.cu: forward, input gradient and weight gradient through 4-D TMA boxes (padding = out-of-bounds
+    zero fill; the weight gradient contracts over pixel boxes) — against torch conv2d in fp32 on the same bf16-rounded operands."""
     from declip_b200 import functions_conv as C_
     torch.manual_seed(B * 1000 + C + H)
     x = torch.randn(B, C, H, H, device=cuda_dev)
@@ -245,4 +245,4 @@ def test_conv3x3_implicit_gemm(cuda_dev, B, C, Cout, H):
     y.backward(_nhwc(g))
     yr.backward(_nhwc(g).float().view(B, H, H, Cout).permute(0, 3, 1, 2))
     assert _rel(_nchw(xh.grad, B, H, H), xr.grad) < 6e-3
-    assert _cos(w.grad, wr.grad) > 0.9995
+    assert _rel(w.grad, wr.grad) < 6e-3
