@@ -293,6 +293,157 @@ __global__ void __launch_bounds__(NV * 32 * (24 / NV)) ln_bwd_group_kernel(
   }
 }
 
+// Third LayerNorm backward: the same thread <-> 8-column ownership and row groups as ln_bwd_group_kernel, but the rows
+// arrive through a 4-stage shared-memory ring filled by a producer warp with cp.async.bulk (a tile of G consecutive rows
+// of x / dy / dres is one contiguous run, so each operand is ONE bulk copy of 12 KiB).  Up to 144 KiB per SM are in flight
+// independent of the consumers' registers — the register-prefetch kernels keep one row (48 B) per thread in flight and sit
+// at 0.4 of the HBM floor.
+template <int NV>
+__global__ void __launch_bounds__(25 * 32, 1) ln_bwd_pipe_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, float* __restrict__ dcol, int rows) {
+  constexpr int W = NV * 256;
+  constexpr int G = 24 / NV;                      // rows per tile = row groups per block
+  constexpr int ST = 4;
+  constexpr int ROWB = W * 2, TILE_B = G * ROWB;  // 12288 for every NV
+  extern __shared__ uint8_t ln_smem_raw[];
+  uint8_t* stg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ln_smem_raw) + 127) & ~uintptr_t(127));
+  float* s_acc = reinterpret_cast<float*>(stg + ST * 3 * TILE_B);
+  float* s_part = s_acc + 3 * W;                  // [2][G][NV][2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_part + 2 * G * NV * 2);
+  uint64_t* empty = full + ST;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 3 * W; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 24); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ntiles = (rows + G - 1) / G;
+  const int nop = dres != nullptr ? 3 : 2;
+  if (warp == 24) {
+    if (lane == 0) {
+      int k = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+        const int s = k % ST;
+        const uint32_t ph = (k / ST) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const int row0 = tile * G;
+        const int nvalid = rows - row0 < G ? rows - row0 : G;
+        const uint32_t bytes = static_cast<uint32_t>(nvalid) * ROWB;
+        mbar_arrive_expect_tx(&full[s], bytes * nop);
+        uint8_t* base = stg + s * 3 * TILE_B;
+        const size_t off = static_cast<size_t>(row0) * W;
+        bulk_load_1d(base, x + off, bytes, &full[s]);
+        bulk_load_1d(base + TILE_B, dy + off, bytes, &full[s]);
+        if (dres != nullptr) bulk_load_1d(base + 2 * TILE_B, dres + off, bytes, &full[s]);
+      }
+    }
+  } else {
+    const int grp = warp / NV, wig = warp - grp * NV;
+    const int col = (wig * 32 + lane) * 8;
+    float g[8], ag[8], ab[8], ao[8];
+    {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; ao[i] = 0.f; }
+    }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+      const int s = k % ST;
+      const uint32_t ph = (k / ST) & 1;
+      const int row = tile * G + grp;
+      const bool valid = row < rows;                 // uniform over the group's warps
+      float mu = 0.f, rs = 0.f;
+      if (valid) { mu = __ldg(mean + row); rs = __ldg(rstd + row); }
+      mbar_wait(&full[s], ph);
+      if (valid) {
+        const uint8_t* base = stg + s * 3 * TILE_B + grp * ROWB + col * 2;
+        const uint4 cx = *reinterpret_cast<const uint4*>(base);
+        const uint4 cdy = *reinterpret_cast<const uint4*>(base + TILE_B);
+        float xv[8], dv[8], xh[8];
+        unpack8(cx, xv);
+        unpack8(cdy, dv);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[i] = (xv[i] - mu) * rs;
+          const float gy = dv[i] * g[i];
+          s1 += gy;
+          s2 = fmaf(gy, xh[i], s2);
+          ag[i] = fmaf(dv[i], xh[i], ag[i]);
+          ab[i] += dv[i];
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (NV > 1) {
+          float* slot = s_part + ((k & 1) * G + grp) * NV * 2;
+          if (lane == 0) { slot[wig * 2] = s1; slot[wig * 2 + 1] = s2; }
+          asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NV * 32) : "memory");
+          s1 = 0.f; s2 = 0.f;
+#pragma unroll
+          for (int q = 0; q < NV; ++q) { s1 += slot[q * 2]; s2 += slot[q * 2 + 1]; }
+        }
+        const float c1 = s1 * (1.0f / W), c2 = s2 * (1.0f / W);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (dv[i] * g[i] - c1 - xh[i] * c2);
+        if (dres != nullptr) {
+          float rv[8];
+          unpack8(*reinterpret_cast<const uint4*>(base + 2 * TILE_B), rv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += rv[i];
+        }
+        if (dcol != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ao[i] += o[i];
+        }
+        uint4 w;
+        w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+        w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(dx + static_cast<size_t>(row) * W + col) = w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_acc[col + i], ag[i]);
+      atomicAdd(&s_acc[W + col + i], ab[i]);
+      if (dcol != nullptr) atomicAdd(&s_acc[2 * W + col + i], ao[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_acc[i]);
+    atomicAdd(&dbeta[i], s_acc[W + i]);
+    if (dcol != nullptr) atomicAdd(&dcol[i], s_acc[2 * W + i]);
+  }
+}
+
+template <int NV>
+static int launch_ln_bwd_pipe(const bf16* dy, const bf16* x, const float* gamma, const float* mean, const float* rstd,
+                              const bf16* dres, bf16* dx, float* dgamma, float* dbeta, float* dcol, int rows, cudaStream_t st) {
+  constexpr int W = NV * 256, G = 24 / NV;
+  constexpr int SMEM = 4 * 3 * 12288 + 3 * W * 4 + 2 * 24 * 2 * 4 + 8 * 8 + 128;
+  auto kern = ln_bwd_pipe_kernel<NV>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(ln_bwd_pipe)", e);
+    attr = true;
+  }
+  int grid = (rows + G - 1) / G;
+  if (grid > sm_count()) grid = sm_count();
+  kern<<<grid, 25 * 32, SMEM, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dcol, rows);
+  return 0;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // Column sums (bias gradients): out[c] += sum_r x[r,c].  Block = 8 column-vectors x 32 row lanes,
 // 64 columns x ROWS_PER_BLOCK rows per block; warp loads are 4 rows x 128 contiguous bytes.
@@ -740,6 +891,19 @@ int dc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const fl
   const bf16* rp = static_cast<const bf16*>(dres);
   bf16* dxp = static_cast<bf16*>(dx);
   static const bool v1 = [] { const char* e = getenv("DC_LN_BWD_V1"); return e != nullptr && e[0] == '1'; }();
+  static const bool v2 = [] { const char* e = getenv("DC_LN_BWD_GROUP"); return e != nullptr && e[0] == '1'; }();
+  if (!v1 && !v2 && (width == 256 || width == 512 || width == 768 || width == 1024)) {
+    int rc;
+    switch (width / 256) {
+      case 1: rc = launch_ln_bwd_pipe<1>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows, st); break;
+      case 2: rc = launch_ln_bwd_pipe<2>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows, st); break;
+      case 3: rc = launch_ln_bwd_pipe<3>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows, st); break;
+      default: rc = launch_ln_bwd_pipe<4>(dyp, xp, gamma, mean, rstd, rp, dxp, dgamma, dbeta, dcol, rows, st); break;
+    }
+    if (rc) return rc;
+    DC_CHECK_LAUNCH("layernorm_bwd");
+    return 0;
+  }
   if (!v1 && (width == 256 || width == 512 || width == 768 || width == 1024)) {
     // warp-group-per-row kernel: one 768-thread block per SM (24 warps), blocks walk the rows with stride grid x groups
     const int nv = width / 256;

@@ -14,7 +14,7 @@ for rows, W in ((25600, 768), (39424, 512)):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ts = []
     for i in range(10):
-        flush.zero_()
+        flush.sum()          # evict with CLEAN lines: a zero_() flush leaves ~126 MB of dirty L2 whose write-back is charged to the timed kernel
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dx, dg, db, dc = ops.layernorm_bwd(dy, x, g, mean, rstd, dres, with_colsum=True)
@@ -30,4 +30,4 @@ for rows, W in ((25600, 768), (39424, 512)):
     print(json.dumps({"rows": rows, "W": W, "us": round(sum(ts) / len(ts), 1), "floor_us": round(rows * W * 2 * 4 / 7.0e6, 1),
                       "dx_maxerr": round(err, 4), "dgamma_cos": round(cg, 6), "dbeta_err": float((db - dy.float().sum(0)).abs().max()),
                       "dcol_err": float((dc - ref.sum(0)).abs().max() / ref.sum(0).abs().max()),
-                      "legacy": os.environ.get("DC_LN_BWD_LEGACY", "0")}))
+                      "mode": "v1" if os.environ.get("DC_LN_BWD_V1") == "1" else ("group" if os.environ.get("DC_LN_BWD_GROUP") == "1" else "pipe")}))
