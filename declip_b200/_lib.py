@@ -119,6 +119,7 @@ SIGNATURES = {
     "dc_bpe_tokenize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int]),
     "dc_conv3x3_igemm_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "dc_conv3x3_igemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dc_conv3x3_wgrad_igemm_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "dc_conv3x3_wgrad_igemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dc_head_workspace_floats": (c_size_t, [c_int, c_int]),
     "dc_head_layout": (c_int, [c_int, c_int, c_void_p]),

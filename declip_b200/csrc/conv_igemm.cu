@@ -29,8 +29,8 @@ struct ConvParams {
   int bh, nb;            // rows of an image / images per pixel tile
   int tiles_y;           // pixel tiles per image (nb == 1) — otherwise 1
   int n_ptiles, n_ctiles;
-  int kblocks;           // 9 * C / 64
-  int cblocks;           // C / 64
+  int kblocks;           // 9 * cblocks
+  int cblocks;           // ceil(C / 64): a 32-channel tensor rides in half-empty boxes (TMA zero fill past the channel dim)
   bf16* out;
 };
 
@@ -80,7 +80,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_arrive_expect_tx(&full_bar[stage], a_tx + B_BYTES);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         tma_load_4d(sa, &tmX, &full_bar[stage], cb * CV_BK, dx, y0 + dy, n0);
-        tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], kb * CV_BK, ct * BN);
+        tma_load_2d(sa + A_BYTES, &tmW, &full_bar[stage], tap * p.C + cb * CV_BK, ct * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -164,7 +164,7 @@ static int launch_conv(const CUtensorMap& tmX, const CUtensorMap& tmW, const Con
 // dW [Cout, 9 * C] (zeroed by the caller).
 struct WgradParams {
   int B, H, W, C, Cout;
-  int bh, tiles_y, rows_per_kb, total_kb, ksplits;
+  int bw, bh, tiles_x, tiles_y, rows_per_kb, total_kb, ksplits;
   int co_tiles, ci_tiles;
   float* dw;
 };
@@ -213,16 +213,19 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_cons
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = split; kb < p.total_kb; kb += p.ksplits) {
-        const int n = kb / p.tiles_y;
-        const int y0 = (kb - n * p.tiles_y) * p.bh;
+        const int txi = kb % p.tiles_x;
+        const int q = kb / p.tiles_x;
+        const int n = q / p.tiles_y;
+        const int y0 = (q - n * p.tiles_y) * p.bh;
+        const int x0 = txi * p.bw;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], tx);
         uint8_t* sa = smem + stage * STAGE_BYTES;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) tma_load_4d(sa + a * 8192, &tmDY, &full_bar[stage], cot * CV_BM + a * 64, 0, y0, n);
+        for (int a = 0; a < 2; ++a) tma_load_4d(sa + a * 8192, &tmDY, &full_bar[stage], cot * CV_BM + a * 64, x0, y0, n);
 #pragma unroll
         for (int b = 0; b < BN / 64; ++b)
-          tma_load_4d(sa + A_BYTES + b * 8192, &tmX, &full_bar[stage], cit * BN + b * 64, dx, y0 + dy, n);
+          tma_load_4d(sa + A_BYTES + b * 8192, &tmX, &full_bar[stage], cit * BN + b * 64, x0 + dx, y0 + dy, n);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -299,12 +302,12 @@ static int launch_wgrad(const CUtensorMap& tmDY, const CUtensorMap& tmX, const W
 using namespace dc;
 
 extern "C" int dc_conv3x3_igemm_supported(int H, int W, int C, int Cout) {
-  return (C % 64 == 0 && Cout % 64 == 0 && W >= 1 && W <= 128 && H >= 1) ? 1 : 0;
+  return (C % 32 == 0 && Cout % 32 == 0 && W >= 1 && W <= 128 && H >= 1) ? 1 : 0;
 }
 
 extern "C" int dc_conv3x3_igemm(const void* x, const void* w, void* out, int batch, int H, int W, int C, int Cout,
                                 dc_stream_t stream) {
-  if (!dc_conv3x3_igemm_supported(H, W, C, Cout)) return set_error("conv3x3_igemm: needs C % 64 == 0, Cout % 64 == 0, W <= 128");
+  if (!dc_conv3x3_igemm_supported(H, W, C, Cout)) return set_error("conv3x3_igemm: needs C % 32 == 0, Cout % 32 == 0, W <= 128");
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.B = batch; p.H = H; p.W = W; p.C = C; p.Cout = Cout;
@@ -319,7 +322,7 @@ extern "C" int dc_conv3x3_igemm(const void* x, const void* w, void* out, int bat
   }
   const int BN = Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64);
   p.n_ctiles = (Cout + BN - 1) / BN;
-  p.cblocks = C / CV_BK;
+  p.cblocks = (C + CV_BK - 1) / CV_BK;
   p.kblocks = 9 * p.cblocks;
   p.out = static_cast<bf16*>(out);
   CUtensorMap tmX, tmW;
@@ -337,16 +340,26 @@ extern "C" int dc_conv3x3_igemm(const void* x, const void* w, void* out, int bat
   return launch_conv<64>(tmX, tmW, p, st);
 }
 
+extern "C" int dc_conv3x3_wgrad_igemm_supported(int H, int W, int C, int Cout) {
+  if (C % 32 != 0 || Cout % 32 != 0 || W < 1 || H < 1) return 0;
+  const int tiles_x = (W + 63) / 64;
+  return (W % tiles_x == 0 && W / tiles_x <= 64) ? 1 : 0;
+}
+
 extern "C" int dc_conv3x3_wgrad_igemm(const void* dy, const void* x, float* dw, int batch, int H, int W, int C, int Cout,
                                       dc_stream_t stream) {
-  if (C % 64 != 0 || Cout % 64 != 0 || W < 1 || W > 64) return set_error("conv3x3_wgrad_igemm: needs C % 64 == 0, Cout % 64 == 0, W <= 64");
+  if (!dc_conv3x3_wgrad_igemm_supported(H, W, C, Cout))
+    return set_error("conv3x3_wgrad_igemm: needs C % 32 == 0, Cout % 32 == 0, W <= 64 or W a multiple of ceil(W / 64)");
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.B = batch; p.H = H; p.W = W; p.C = C; p.Cout = Cout;
-  p.bh = 64 / W; if (p.bh > H) p.bh = H; if (p.bh < 1) p.bh = 1;
+  p.tiles_x = (W + 63) / 64;
+  p.bw = W / p.tiles_x;
+  p.bh = 64 / p.bw; if (p.bh > H) p.bh = H; if (p.bh < 1) p.bh = 1;
+  if (p.tiles_x > 1) p.bh = 1;
   p.tiles_y = (H + p.bh - 1) / p.bh;
-  p.rows_per_kb = W * p.bh;
-  p.total_kb = batch * p.tiles_y;
+  p.rows_per_kb = p.bw * p.bh;
+  p.total_kb = batch * p.tiles_y * p.tiles_x;
   const int BN = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   p.co_tiles = (Cout + CV_BM - 1) / CV_BM;
   p.ci_tiles = (C + BN - 1) / BN;
@@ -357,7 +370,7 @@ extern "C" int dc_conv3x3_wgrad_igemm(const void* dy, const void* x, float* dw, 
   p.ksplits = ks;
   p.dw = dw;
   CUtensorMap tmDY, tmX;
-  const int box[4] = {64, W, p.bh, 1};
+  const int box[4] = {64, p.bw, p.bh, 1};
   {
     const long long dims[4] = {Cout, W, H, batch};
     const long long strides[3] = {static_cast<long long>(Cout) * 2, static_cast<long long>(W) * Cout * 2,

@@ -91,10 +91,10 @@ def _conv3x3_shadows(weight):
 
 
 class Conv3x3(torch.autograd.Function):
-    """3x3 / pad 1 / stride 1 convolution on NHWC (modified_resnet.py:23,151-154).  C, Cout multiples of 64: implicit GEMM
-    (csrc/conv_igemm.cu) for the forward AND the input gradient — the activation tile of each (tap, channel block) is one
-    4-D TMA box, no [rows, 9C] matrix is written in either direction; the weight gradient still contracts over an
-    im2col matrix (recomputed).  Other channel counts (the 32-channel stem): im2col + GEMM, col2im for the dgrad."""
+    """3x3 / pad 1 / stride 1 convolution on NHWC (modified_resnet.py:23,151-154).  C, Cout multiples of 32 (every conv of
+    the tower, the 32-channel stem included): implicit GEMM (csrc/conv_igemm.cu) for the forward, the input gradient (same
+    kernel, flipped / transposed weights) and the weight gradient (contraction over pixel boxes) — no [rows, 9C] matrix is
+    written in any direction.  Other shapes: im2col + GEMM, col2im for the dgrad."""
 
     @staticmethod
     def forward(ctx, x, weight, B, H, W):
@@ -121,7 +121,8 @@ class Conv3x3(torch.autograd.Function):
         lib = ops.lib_for(x)
         B, H, W, C, cout, igemm = ctx.geom
         dy = dy.contiguous()
-        if igemm and W <= 64 and os.environ.get("DECLIP_B200_CONV_WGRAD", "igemm") == "igemm":
+        if (igemm and lib.dc_conv3x3_wgrad_igemm_supported(H, W, C, cout)
+                and os.environ.get("DECLIP_B200_CONV_WGRAD", "igemm") == "igemm"):
             # contraction over spatial TMA boxes of dy and (shifted) x: no im2col matrix for the weight gradient either
             dw = torch.zeros(cout, 9 * C, device=x.device, dtype=torch.float32)
             _lib.check(lib.dc_conv3x3_wgrad_igemm(_p(dy), _p(x), _p(dw), B, H, W, C, cout, _stream()), "dc_conv3x3_wgrad_igemm")

@@ -260,7 +260,9 @@ int dc_attnpool_assemble_bwd(const void* dtokens, void* dx, int batch, int P, in
 int dc_conv3x3_igemm_supported(int H, int W, int C, int Cout);
 int dc_conv3x3_igemm(const void* x, const void* w, void* out, int batch, int H, int W, int C, int Cout, dc_stream_t stream);
 /* dw[Cout, 9*C] (fp32, (ky, kx, c) order) += sum over pixels of dy[p, co] * x[p + tap offset, ci]: the contraction runs over
- * spatial TMA boxes of both NHWC tensors (MN-major operands), split over CTAs with fp32 atomics.  W <= 64. */
+ * spatial TMA boxes of both NHWC tensors (MN-major operands), split over CTAs with fp32 atomics.  C, Cout multiples of 32
+ * (32-channel tensors ride in half-empty 64-channel boxes); rows wider than 64 pixels are cut into equal parts. */
+int dc_conv3x3_wgrad_igemm_supported(int H, int W, int C, int Cout);
 int dc_conv3x3_wgrad_igemm(const void* dy, const void* x, float* dw, int batch, int H, int W, int C, int Cout,
                            dc_stream_t stream);
 

@@ -227,7 +227,7 @@ def test_bottleneck_block_isolated(cuda_dev, inplanes, planes, stride, H):
 
 
 @pytest.mark.parametrize("B,C,Cout,H", [(3, 64, 64, 56), (2, 128, 128, 28), (5, 256, 256, 14), (5, 512, 512, 7), (3, 64, 128, 56),
-                                        (1, 128, 64, 28), (7, 512, 512, 7)])
+                                        (1, 128, 64, 28), (7, 512, 512, 7), (2, 32, 32, 112), (1, 32, 64, 112), (3, 64, 32, 20)])
 def test_conv3x3_implicit_gemm(cuda_dev, B, C, Cout, H):
     """csrc/conv_igemm.cu: forward, input gradient and weight gradient through 4-D TMA boxes (padding = out-of-bounds
     zero fill; the weight gradient contracts over pixel boxes) — against torch conv2d in fp32 on the same bf16-rounded operands."""
