@@ -139,6 +139,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "dc_token_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "dc_groupmax_mean_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dc_groupmax_mean_bwd_ex": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "dc_groupmax_mean_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "dc_add_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "dc_im2col_stem": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -353,8 +353,9 @@ __global__ void __launch_bounds__(256) groupmax_mean_fwd_kernel(const float* __r
 
 // dG[i*n + j, l*group + m] = (m == arg) ? dout[i, l] / n : 0   (bf16, feeds the two backward GEMMs)
 __global__ void __launch_bounds__(256) groupmax_mean_bwd_kernel(const float* __restrict__ dout, int ldd,
-                                                                const uint8_t* __restrict__ arg, int n, int group,
-                                                                int ncand, bf16* __restrict__ dG, int ldg, int rows) {
+                                                                const uint8_t* __restrict__ arg, int lda, int n,
+                                                                int group, int ncand, bf16* __restrict__ dG, int ldg,
+                                                                int rows) {
   const size_t total = static_cast<size_t>(rows) * ncand;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const float invn = 1.0f / n;
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(256) groupmax_mean_bwd_kernel(const float* __r
     const int l = static_cast<int>(t - r * ncand);
     const int i = static_cast<int>(r / n);
     const float g = dout[static_cast<size_t>(i) * ldd + l] * invn;
-    const int a = arg[t];
+    const int a = arg[r * lda + l];
     bf16* d = dG + r * ldg + static_cast<size_t>(l) * group;
     for (int m = 0; m < group; m += 2)
       *reinterpret_cast<uint32_t*>(d + m) = pack_bf16x2(m == a ? g : 0.f, m + 1 == a ? g : 0.f);
@@ -413,11 +414,16 @@ int dc_groupmax_mean_fwd(const float* G, int ldg, int batch, int n, int group, i
 
 int dc_groupmax_mean_bwd(const float* dout, int ldd, const unsigned char* arg, int batch, int n, int group, int ncand,
                          void* dG, int ldg, dc_stream_t stream) {
+  return dc_groupmax_mean_bwd_ex(dout, ldd, arg, ncand, batch, n, group, ncand, dG, ldg, stream);
+}
+
+int dc_groupmax_mean_bwd_ex(const float* dout, int ldd, const unsigned char* arg, int lda, int batch, int n, int group,
+                            int ncand, void* dG, int ldg, dc_stream_t stream) {
   if (batch <= 0 || ncand <= 0) return 0;
   if (group & 1) return dc::set_error("groupmax: group must be even");
   const int rows = batch * n;
   groupmax_mean_bwd_kernel<<<dc::grid_cap(static_cast<size_t>(rows) * ncand, 256), 256, 0,
-                             static_cast<cudaStream_t>(stream)>>>(dout, ldd, arg, n, group, ncand,
+                             static_cast<cudaStream_t>(stream)>>>(dout, ldd, arg, lda, n, group, ncand,
                                                                   static_cast<dc::bf16*>(dG), ldg, rows);
   DC_CHECK_LAUNCH("groupmax_mean_bwd");
   return 0;

@@ -6,6 +6,7 @@ feature gradients (the reference all-reduces the full [W,b,D] gradient and slice
 W x fewer bytes kept).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -622,11 +623,27 @@ class FilipLate(torch.autograd.Function):
         lib = ops.lib_for(d16)
         batch, n, group, ncand = ctx.meta
         dout = dout.float().contiguous()
-        dG = torch.empty(batch * n, ncand * group, device=d16.device, dtype=torch.bfloat16)
-        _lib.check(lib.dc_groupmax_mean_bwd(_PTR(dout.data_ptr()), dout.stride(0), _PTR(arg.data_ptr()), batch, n, group,
-                                            ncand, _PTR(dG.data_ptr()), dG.stride(0), _stream()), "dc_groupmax_mean_bwd")
-        dd = ops.gemm(dG, sel16, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s)      # [B*n, dim]
-        dsel = ops.gemm(dG, d16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s)   # [N*group, dim]
+        # The backward GEMMs contract over the one-hot operand dG[r, l * group + m] = [m == arg[r, l]] * dout[i(r), l] / n.
+        # It is built per BLOCK of candidates (<= 512 MiB of bf16, DECLIP_B200_FILIP_CHUNK overrides the block size):
+        # dd accumulates over the blocks, dsel's row blocks are independent — at N = 4096 gathered candidates the
+        # full [B*n, N*group] operand would be 3.3 GB per rank, the block is 0.4 GB at every world size.
+        rows, dim = batch * n, d16.shape[1]
+        cb = int(os.environ.get("DECLIP_B200_FILIP_CHUNK", "0")) or max(64, (512 << 20) // (rows * group * 2) // 64 * 64)
+        cb = min(ncand, max(8, cb // 8 * 8))
+        dG = torch.empty(rows, cb * group, device=d16.device, dtype=torch.bfloat16)
+        dd = None
+        dsel = torch.empty(ncand * group, dim, device=d16.device, dtype=torch.float32)
+        for c0 in range(0, ncand, cb):
+            nc = min(cb, ncand - c0)
+            blk = dG if nc == cb else dG.view(-1)[:rows * nc * group].view(rows, nc * group)
+            _lib.check(lib.dc_groupmax_mean_bwd_ex(_PTR(dout.data_ptr() + 4 * c0), dout.stride(0), _PTR(arg.data_ptr() + c0),
+                                                   arg.stride(0), batch, n, group, nc, _PTR(blk.data_ptr()), blk.stride(0),
+                                                   _stream()), "dc_groupmax_mean_bwd")
+            sel_blk = sel16[c0 * group:(c0 + nc) * group]
+            part = ops.gemm(blk, sel_blk, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s)            # [B*n, dim]
+            dd = part if dd is None else dd.add_(part)
+            ops.gemm(blk, d16, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32, alpha_dev=s,
+                     out=dsel[c0 * group:(c0 + nc) * group])                                          # [nc*group, dim]
         # d logit_scale_dense = sum(dout * out): out is linear in s = exp(ls), so d out / d ls = out
         acc = torch.zeros(1, device=d16.device, dtype=torch.float32)
         dot_into(dout, out, acc)

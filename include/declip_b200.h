@@ -225,6 +225,11 @@ int dc_groupmax_mean_fwd(const float* G, int ldg, int batch, int n, int group, i
 /* dG (bf16 [batch*n, ncand*group]) = one-hot(arg) * dout[i,l] / n */
 int dc_groupmax_mean_bwd(const float* dout, int ldd, const unsigned char* arg, int batch, int n, int group, int ncand,
                          void* dG, int ldg, dc_stream_t stream);
+/* the same for a block of candidate columns: `arg` and `dout` point at the block's first column, `lda` / `ldd` are the row
+ * strides of the full matrices — the backward walks the candidates in blocks so the one-hot operand stays bounded
+ * (<= 512 MiB) however many ranks contribute candidates */
+int dc_groupmax_mean_bwd_ex(const float* dout, int ldd, const unsigned char* arg, int lda, int batch, int n, int group,
+                            int ncand, void* dG, int ldg, dc_stream_t stream);
 int dc_add_rows_f32(const float* src, const int* idx, float* dst, int n, int width, dc_stream_t stream);
 
 /* ------------------------------------------------------------------ ModifiedResNet support (modified_resnet.py)

@@ -33,3 +33,26 @@ def test_groupmax_and_scores_ops(cuda_dev):
     assert _cos(out, ref) > 0.9995
     assert _cos(g_d, d1.grad) > 0.98 and _cos(g_s, sel.grad) > 0.98
     assert abs(g_l.item() - ls.grad.item()) < 0.05 * abs(ls.grad.item()) + 1e-2
+
+
+def test_filip_late_backward_in_candidate_blocks(cuda_dev, monkeypatch):
+    """functions.FilipLate.backward walks the gathered candidates in blocks (bounded one-hot operand): three blocks of 8
+    candidates must give the gradients of the single-block pass (fp32 partial sums of dd are added in a different order:
+    relative 1e-5)."""
+    from declip_b200 import functions as F_
+    torch.manual_seed(1)
+    B, n, dim, k = 24, 20, 256, 16
+    d = torch.nn.functional.normalize(torch.randn(B * n, dim, device=cuda_dev), dim=1)
+    sel = torch.nn.functional.normalize(torch.randn(B * k, dim, device=cuda_dev), dim=1)
+    w = torch.randn(B, B, device=cuda_dev)
+    grads = []
+    for chunk in ("0", "8"):
+        monkeypatch.setenv("DECLIP_B200_FILIP_CHUNK", chunk)
+        d1, s1 = d.clone().requires_grad_(True), sel.clone().requires_grad_(True)
+        ls = torch.tensor(1.5, device=cuda_dev, requires_grad=True)
+        (F_.FilipLate.apply(d1, s1, ls, n, k) * w).sum().backward()
+        grads.append((d1.grad.clone(), s1.grad.clone(), ls.grad.clone()))
+    (gd0, gs0, gl0), (gd1, gs1, gl1) = grads
+    assert (gd0 - gd1).abs().max() <= 1e-5 * gd0.abs().max() + 1e-7
+    assert torch.equal(gs0, gs1)
+    assert torch.equal(gl0, gl1)

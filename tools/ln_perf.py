@@ -46,6 +46,25 @@ for rows, W in ((25600, 768), (39424, 512)):
     torch.nn.functional.layer_norm(xf, (W,), g, b, 1e-5).backward(dy.float())
     ref = xf.grad + dres.float()
     nbytes = rows * W * 2 * 4
+    # forward, same protocol (reads x, writes y: 2 passes)
+    ys = [torch.empty_like(s_[0]) for s_ in sets]
+
+    def fwd(i):
+        mean, rstd = stats[i % 4]
+        rc = lib.dc_layernorm_fwd(P(sets[i % 4][0]), P(g), P(b), P(ys[i % 4]), P(mean), P(rstd), rows, W, ctypes.c_float(1e-5), st)
+        assert rc == 0
+
+    for i in range(8):
+        fwd(i)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(N):
+        fwd(i)
+    f1.record(); torch.cuda.synchronize()
+    fus = f0.elapsed_time(f1) * 1e3 / N
+    print(json.dumps({"rows": rows, "W": W, "mode": "fwd", "us": round(fus, 1), "GBps": round(nbytes / 2 / fus / 1e3, 0),
+                      "floor_us_at_6584GBps": round(nbytes / 2 / 6584.5e3, 1)}))
     print(json.dumps({"rows": rows, "W": W, "mode": mode, "us": round(us, 1), "GBps": round(nbytes / us / 1e3, 0),
                       "floor_us_at_6584GBps": round(nbytes / 6584.5e3, 1), "dx_maxerr": round(float((dx.float() - ref).abs().max()), 4),
                       "dbeta_err": float((db - dy.float().sum(0)).abs().max()),
