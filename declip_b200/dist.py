@@ -60,6 +60,7 @@ class DistModule(Module):
         self._stage = {}          # id(rt) -> bf16 staging buffer (one per tower, same layout as grad_flat)
         self._reserved = False
         self.broadcast_params()
+        overlap = overlap and os.environ.get("DECLIP_B200_OVERLAP", "1") != "0"      # A/B switch (tools/gpu_round2x_n2.sh)
         if overlap and get_world_size() > 1:
             for rt in self._runtimes():
                 rt.grad_ready_hook = self._on_tower_grads_ready
@@ -187,6 +188,8 @@ class DistModule(Module):
         """dist.py:76-83 equivalent: SUM-all-reduce every gradient, then make the result visible to the
         optimizer stream (no device-wide synchronize)."""
         if get_world_size() == 1:
+            return
+        if os.environ.get("DECLIP_B200_SKIP_GRAD_SYNC") == "1":      # measurement only: the step WITHOUT its all-reduce
             return
         err = getattr(self, "_cb_error", None)
         if err is not None:
