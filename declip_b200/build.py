@@ -59,10 +59,14 @@ def build(verbose=False, force=False):
         print(log)
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+        tmp = OUT + ".tmp.%d" % os.getpid()        # link beside the target, then rename: readers never see a partial file
+        cmd = [NVCC] + ARCH + ["-shared", "-o", tmp] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        os.replace(tmp, OUT)
     return OUT
 
 

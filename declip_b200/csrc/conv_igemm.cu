@@ -13,7 +13,8 @@
 //
 // Launch: one CTA per (pixel tile, 64..256-wide Cout block), 192 threads: warp 0 TMA producer, warp 1 tcgen05.mma issuer
 // + TMEM allocation, warps 2-5 epilogue (one output pixel per thread, bf16 stores of 64-byte channel segments).  Two
-// CTAs fit an SM (<= 96 KiB of stages, <= 256 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
+// CTAs fit an SM (<= 96 KiB of stages, <= 256 TMEM columns each; three for the 64-wide tile), so one CTA's epilogue
+// overlaps the others' main loops and the 9-k-block pipeline drain of a small-channel tile is hidden behind its neighbours.
 #include <string.h>
 #include "common.cuh"
 #include "internal.h"
@@ -35,7 +36,7 @@ struct ConvParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(CV_THREADS, 2)
+__global__ void __launch_bounds__(CV_THREADS, BN == 64 ? 3 : 2)      // 64-wide tiles: 3 x 73 KiB of stages fit, one more tile in flight
 conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const ConvParams p) {
   constexpr int STAGES = BN == 256 ? 2 : 3;
   constexpr int A_BYTES = CV_BM * CV_BK * 2;
