@@ -24,6 +24,7 @@
 // columns, its K slice is identically zero (rows of dS sum to zero) and its V slice equals colsum(dO), which the
 // caller gets for free from the epilogue of the GEMM that produces dO (or from this kernel with db_v = 1).
 // Outputs leave through per-warp staged TMA stores (scattered 16-byte global stores made the LSU the bottleneck).
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "internal.h"
@@ -493,6 +494,290 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Forward, two CTAs per SM [r2] — the default forward (ViT b = 512: 42.7 -> 31.0 us under ncu, text 59 -> 45 us with CUDA
+// events; profiles/r02_attention_fwd2.md).  The kernel above keeps ONE tile in flight per CTA: load -> S -> softmax -> P V
+// -> epilogue is a serial chain (2.3 us per ViT tile; ncu: 21 % of the warp samples sit in the o_full wait, the rest is
+// spread thinly over the chain, tensor pipe 16 % busy, DRAM at half of its peak) and its 160 KiB of shared memory
+// (double-buffered Q / K / V) admit one CTA per SM.  This variant is the same tile algorithm with a footprint of 99 KiB
+// and <= 128 registers, so that TWO CTAs are resident per SM and one CTA's softmax / epilogue runs under the other's UMMA
+// and TMA phases:
+//   * Q, K, V are single-buffered, but each is re-filled the moment its last reader finished: Q and K of the next tile are
+//     requested right after `s_full` (the S UMMAs have read them), V right after `o_full` — separate mbarriers `ld_qk` /
+//     `ld_v`, so a load is in flight during the whole softmax + P V + epilogue span of the current tile;
+//   * the score chunk is read from TMEM twice (row maximum, then exponentials) instead of being parked in 64 registers;
+//   * one 2 KiB output staging buffer per warp (a warp stores one 32 x 32 chunk per tile);
+//   * the next tile's S UMMAs are issued right after this tile's P V if its Q / K have landed (non-blocking
+//     `mbarrier.test_wait`), else after the epilogue — the issuing warp never parks in front of its own epilogue.
+struct Attn2Smem {
+  static constexpr uint32_t P_OFF = 3 * AT_TILE_BYTES;                  // Q | K | V | P (2 blocks)
+  static constexpr uint32_t STAGE_OFF = P_OFF + 2 * AT_TILE_BYTES;      // 8 warps x 2 KiB output staging
+  static constexpr uint32_t TAIL_OFF = STAGE_OFF + 8 * 2048;
+  static constexpr uint32_t XCHG_BYTES = 2 * 2 * 128 * 4;               // [which][half][row]
+  static constexpr uint32_t BAR_OFF = TAIL_OFF + XCHG_BYTES;
+  static constexpr uint32_t TOTAL = BAR_OFF + 16 * 8 + 1024;            // + alignment slack
+};
+static_assert(2 * (Attn2Smem::TOTAL + 1024) <= 233472, "two forward CTAs must fit one SM's shared memory");
+
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {   // non-blocking poll
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOUT, const AttnTcParams p) {
+  using SM = Attn2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * AT_TILE_BYTES;
+  uint8_t* sP = smem + SM::P_OFF;
+  float* xa = reinterpret_cast<float*>(smem + SM::TAIL_OFF);   // [2][128] row maxima of the two warps of a quadrant
+  float* xb = xa + 256;                                         // [2][128] row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* ld_qk = bars;          // Q and K of a tile landed
+  uint64_t* ld_v = bars + 1;       // V of a tile landed
+  uint64_t* s_full = bars + 2;     // S = Q K^T complete (Q, K buffers free)
+  uint64_t* p_ready = bars + 3;    // all 8 warps wrote P and are done with S and the previous O
+  uint64_t* o_full = bars + 4;     // O = P V complete (V buffer and P free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 256;
+  if (threadIdx.x == 0) {
+    mbar_init(ld_qk, 1); mbar_init(ld_v, 1);
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1);
+    fence_mbar_init();
+    prefetch_tensormap(&tmQKV);
+    prefetch_tensormap(&tmOUT);
+  }
+  // P starts as zeros: regions no warp ever writes (cross-pair blocks, fully masked causal chunks, rows >= L of quadrants
+  // without work) must read as exact zeros in every tile
+  for (uint32_t i = threadIdx.x; i < 2u * AT_TILE_BYTES / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const int grp = blockIdx.x % p.groups;   // head group of this CTA
+  const int b0 = blockIdx.x / p.groups;    // first sample; then += per_group
+  const int stride = p.per_group;
+
+  auto issue_qk = [&](int b) {
+    mbar_arrive_expect_tx(ld_qk, 2 * AT_TILE_BYTES);
+    for (int slot = 0; slot < p.pp; ++slot) {
+      const int h = grp * p.pp + slot;
+      const uint32_t off = slot * p.rp * 128;
+      tma_load_4d(sQ + off, &tmQKV, ld_qk, 0, h, 0, b);
+      tma_load_4d(sK + off, &tmQKV, ld_qk, 0, p.heads + h, 0, b);
+    }
+  };
+  auto issue_v = [&](int b) {
+    mbar_arrive_expect_tx(ld_v, AT_TILE_BYTES);
+    for (int slot = 0; slot < p.pp; ++slot)
+      tma_load_4d(sV + slot * p.rp * 128, &tmQKV, ld_v, 0, 2 * p.heads + grp * p.pp + slot, 0, b);
+  };
+  auto issue_s = [&]() {     // S = Q K^T
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tS, umma_smem_desc(aQ + k * 32, 16, 1024), umma_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0);
+    umma_commit(s_full);
+  };
+  auto issue_o = [&]() {     // O = P V
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, false, true);
+    const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      umma_bf16(tO, umma_smem_desc(aP + (s >> 2) * AT_TILE_BYTES + (s & 3) * 32, 16, 1024),
+                umma_smem_desc(aV + s * 2048, AT_TILE_BYTES, 1024), idesc_o, s > 0);
+    umma_commit(o_full);
+  };
+
+  const int q = warp & 3;     // TMEM lane quadrant of this warp
+  const int hf = warp >> 2;   // which of the two warps of the quadrant
+  const int row = q * 32 + lane;
+  const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+  const int slot = (p.pp == 2) ? (row >> 6) : 0;
+  const int l = (p.pp == 2) ? (row & 63) : row;
+  const bool row_valid = l < p.L;
+  int nch = 0, ch0 = 0, ch1 = 0;     // 32-column chunks of the score tile owned by this warp (warp-uniform)
+  if (p.pp == 2) {
+    if ((q & 1) * 32 < p.L) { nch = 1; ch0 = slot * 2 + hf; }
+  } else if (q * 32 < p.L) {
+    const int need = (p.L + 31) >> 5;
+    const int ntot = p.causal ? min(q + 1, need) : need;
+    if (hf < ntot) { ch0 = hf; nch = 1; }
+    if (hf + 2 < ntot) { ch1 = hf + 2; nch = 2; }
+  }
+  const float kScaleLog2 = 0.125f * 1.4426950408889634f;
+  const float kLn2 = 0.6931471805599453f;
+  const int h = grp * p.pp + slot;   // this thread's head (fixed for the whole kernel)
+  const int l0 = (p.pp == 2) ? (q & 1) * 32 : q * 32;   // sequence position of this warp's first row
+  const bool warp_rows = l0 < p.L;
+  uint8_t* wstage = smem + SM::STAGE_OFF + warp * 2048;
+  auto chunk_mask = [&](int c) -> uint32_t {   // bit j = column j of chunk c participates in this thread's row
+    if (!row_valid) return 0u;
+    const int key0 = (p.pp == 2) ? (c & 1) * 32 : c * 32;
+    int lim = p.L;
+    if (p.causal) lim = min(lim, l + 1);
+    const int n = lim - key0;
+    return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+  };
+  const uint32_t mask0 = nch > 0 ? chunk_mask(ch0) : 0u;
+  const uint32_t mask1 = nch > 1 ? chunk_mask(ch1) : 0u;
+
+  if (warp == 1) {
+    if (elect_one()) {
+      if (b0 < p.batch) { issue_qk(b0); issue_v(b0); }
+    }
+    __syncwarp();
+  }
+  if (warp == 0) {
+    if (elect_one()) {
+      if (b0 < p.batch) {
+        mbar_wait(ld_qk, 0);
+        tc_fence_after();
+        issue_s();
+      }
+    }
+    __syncwarp();
+  }
+
+  int it = 0;
+  for (int b = b0; b < p.batch; b += stride, ++it) {
+    const bool has_next = b + stride < p.batch;
+    const uint32_t par = it & 1;
+    mbar_wait(s_full, par);
+    tc_fence_after();
+    if (warp == 1) {           // Q / K are free: fetch the next tile's
+      if (elect_one()) {
+        if (has_next) issue_qk(b + stride);
+      }
+      __syncwarp();
+    }
+    // ---------------------------------------------------------------- softmax: row maximum, then exponentials -> P
+    float mx = -INFINITY;
+    auto max_chunk = [&](int c, uint32_t msk) {
+      uint32_t raw[32];
+      tmem_ld32(tS + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      asm volatile("" : "+r"(msk));   // keep the per-column tests out of the loop-invariant hoister (register pressure)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, ((msk >> j) & 1u) ? __uint_as_float(raw[j]) : -INFINITY);
+    };
+    if (nch > 0) max_chunk(ch0, mask0);
+    if (nch > 1) max_chunk(ch1, mask1);
+    xa[hf * 128 + row] = mx;
+    named_bar_sync(1 + q, 64);
+    float m = fmaxf(xa[row], xa[128 + row]) * kScaleLog2;   // the scale is positive: max commutes with it
+    if (!(m > -INFINITY)) m = 0.f;
+    float sum = 0.f;
+    auto exp_chunk = [&](int c, uint32_t msk) {
+      uint32_t raw[32], pk[16];
+      tmem_ld32(tS + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      asm volatile("" : "+r"(msk));
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float p0 = ((msk >> j) & 1u) ? ex2_approx(fmaf(__uint_as_float(raw[j]), kScaleLog2, -m)) : 0.f;
+        const float p1 = ((msk >> (j + 1)) & 1u) ? ex2_approx(fmaf(__uint_as_float(raw[j + 1]), kScaleLog2, -m)) : 0.f;
+        sum += p0 + p1;
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      store_chunk_sw128(sP, row, c, pk);
+    };
+    if (nch > 0) exp_chunk(ch0, mask0);
+    if (nch > 1) exp_chunk(ch1, mask1);
+    xb[hf * 128 + row] = sum;
+    named_bar_sync(1 + q, 64);
+    const float tot = xb[row] + xb[128 + row];
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_ready);
+    // ---- UMMA issuer: O = P V; then the next tile's S if its Q / K are already here
+    bool s_issued = false;
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_wait(p_ready, par);
+        mbar_wait(ld_v, par);
+        tc_fence_after();
+        issue_o();
+        if (has_next && mbar_test_wait(ld_qk, par ^ 1u)) {
+          tc_fence_after();
+          issue_s();
+          s_issued = true;
+        }
+      }
+      __syncwarp();
+    }
+    mbar_wait(o_full, par);
+    tc_fence_after();
+    if (warp == 1) {           // V is free: fetch the next tile's
+      if (elect_one()) {
+        if (has_next) issue_v(b + stride);
+      }
+      __syncwarp();
+    }
+    // ---------------------------------------------------------------- epilogue: O / rowsum -> out, log-sum-exp
+    if (warp_rows) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_base + hf * 32, o);
+      tmem_ld_wait();
+      const float inv = 1.0f / fmaxf(tot, 1e-30f);
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        pk[j] = pack_bf16x2(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv);
+      if (lane == 0) bulk_wait_read0();      // this warp's previous store has read the staging buffer
+      __syncwarp();
+      uint8_t* rowp = wstage + lane * 64;
+      const int sw = (lane >> 1) & 3;        // CU_TENSOR_MAP_SWIZZLE_64B
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmOUT, wstage, h * 64 + hf * 32, l0, b);
+        bulk_commit();
+      }
+      if (row_valid && hf == 0 && p.lse != nullptr)
+        p.lse[(static_cast<size_t>(b) * p.heads + h) * p.L + l] = (m + __log2f(fmaxf(tot, 1e-30f))) * kLn2;
+    }
+    tc_fence_before();   // orders this tile's tcgen05.ld before the p_ready arrive of the next tile
+    if (warp == 0) {     // the next tile's S, if its operands were still in flight above
+      if (elect_one()) {
+        if (has_next && !s_issued) {
+          mbar_wait(ld_qk, par ^ 1u);
+          tc_fence_after();
+          issue_s();
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) bulk_wait_read0();   // the staging buffers must stay valid until the last stores have read them
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 template <bool BWD>
 static int launch_attn_tc(const void* qkv, const void* dout, AttnTcParams p, cudaStream_t st) {
   if (p.L <= 0 || p.L > 128 || p.heads > AT_MAX_HEADS) return DC_ATTN_TC_UNSUPPORTED;
@@ -547,11 +832,58 @@ static int launch_attn_tc(const void* qkv, const void* dout, AttnTcParams p, cud
   return 0;
 }
 
+// Forward through the two-CTAs-per-SM kernel (the default; DC_ATTN_FWD_V1=1 selects the one-tile-per-SM kernel above).
+static int launch_attn_fwd2(const void* qkv, AttnTcParams p, cudaStream_t st) {
+  if (p.L <= 0 || p.L > 128 || p.heads > AT_MAX_HEADS) return DC_ATTN_TC_UNSUPPORTED;
+  p.pp = p.L <= 64 ? 2 : 1;
+  p.rp = 128 / p.pp;
+  if (p.heads % p.pp != 0) return DC_ATTN_TC_UNSUPPORTED;
+  p.groups = p.heads / p.pp;
+  if (p.groups > sm_count()) return DC_ATTN_TC_UNSUPPORTED;
+  p.D = p.heads * 64;
+  auto kern = attn_tc_fwd2_kernel;
+  constexpr size_t smem = Attn2Smem::TOTAL;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_tc_fwd2)", e);
+    // two CTAs only fit with the full shared-memory carve-out (with the default preference the occupancy query — sized for
+    // one block — answered 1 and the first version of this launcher ran one CTA per SM)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_error_cuda("cudaFuncSetAttribute(attn_tc_fwd2 carveout)", e);
+    set = true;
+  }
+  // 2 CTAs per SM by construction: __launch_bounds__(256, 2) caps the registers, the static_assert above the shared memory,
+  // 2 x 256 TMEM columns; if a device admitted only one, the second half of the grid would simply run as a second wave
+  p.per_group = 2 * sm_count() / p.groups;
+  if (p.per_group > p.batch) p.per_group = p.batch;
+  CUtensorMap tmQKV, tmOUT;
+  {
+    const long long dims[4] = {64, 3LL * p.heads, p.L, p.batch};
+    const long long strides[3] = {128, 3LL * p.D * 2, static_cast<long long>(p.L) * 3 * p.D * 2};
+    const int box[4] = {64, 1, p.rp, 1};
+    int rc = make_tmap_4d(&tmQKV, qkv, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const long long dims[3] = {p.D, p.L, p.batch};
+    const long long strides[2] = {static_cast<long long>(p.D) * 2, static_cast<long long>(p.L) * p.D * 2};
+    const int box[3] = {32, 32, 1};
+    int rc = make_tmap_nd(&tmOUT, p.out, 3, dims, strides, box, 64);
+    if (rc) return rc;
+  }
+  kern<<<p.groups * p.per_group, AT_THREADS, smem, st>>>(tmQKV, tmOUT, p);
+  DC_CHECK_LAUNCH("attention_tc_fwd2");
+  return 0;
+}
+
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int L, int heads, int causal, cudaStream_t st) {
   AttnTcParams p{};
   p.L = L; p.heads = heads; p.batch = batch; p.causal = causal;
   p.lse = lse; p.out = static_cast<bf16*>(out);
-  return launch_attn_tc<false>(qkv, nullptr, p, st);
+  static const bool v1 = [] { const char* e = getenv("DC_ATTN_FWD_V1"); return e != nullptr && e[0] == '1'; }();
+  if (v1) return launch_attn_tc<false>(qkv, nullptr, p, st);      // the one-tile-per-SM forward (A/B, fallback)
+  return launch_attn_fwd2(qkv, p, st);
 }
 
 bool attention_tc_supported(int batch, int L, int heads) {

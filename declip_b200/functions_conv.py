@@ -70,6 +70,38 @@ class Conv1x1(torch.autograd.Function):
         return dx, dw
 
 
+class Conv1x1Skip(torch.autograd.Function):
+    """conv1 of a Bottleneck together with the block's skip connection (modified_resnet.py:40-56: `identity = x` next to
+    `self.conv1(x)`): returns (conv1(x), x).  Routing the identity branch through the second output hands its gradient to
+    THIS backward, where the input-gradient GEMM adds it in its epilogue (fp32 accumulator + bf16 aux, one rounding) —
+    instead of autograd materialising both branch gradients and summing them in a separate elementwise pass
+    (16 launches, 2.6 ms of the res50 step, 6 B/element of HBM traffic)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        ctx.set_materialize_grads(False)      # an unused output's gradient stays None instead of a zero tensor
+        w16 = weight_shadow(weight).view(weight.shape[0], -1)
+        y = ops.gemm(x, w16)
+        ctx.save_for_backward(x, w16)
+        ctx.wshape = tuple(weight.shape)
+        return y, x.detach()          # same storage; as an output of this node it carries the skip branch's gradient back here
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, w16 = ctx.saved_tensors
+        dx = None
+        if dy is None:                # only the skip branch was used
+            return dskip, None
+        dy = dy.contiguous()
+        if ctx.needs_input_grad[0]:
+            if dskip is not None:
+                dx = ops.gemm(dy, w16, b_mn_major=True, epilogue=ops.EPI_BF16_RESID, aux=dskip.contiguous())
+            else:
+                dx = ops.gemm(dy, w16, b_mn_major=True)
+        dw = ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, epilogue=ops.EPI_F32_ATOMIC).reshape(ctx.wshape)
+        return dx, dw
+
+
 def _igemm_conv(lib, x, w_flat, B, H, W, C, cout):
     y = torch.empty(B * H * W, cout, device=x.device, dtype=torch.bfloat16)
     _lib.check(lib.dc_conv3x3_igemm(_p(x), _p(w_flat), _p(y), B, H, W, C, cout, _stream()), "dc_conv3x3_igemm")

@@ -47,7 +47,8 @@ class Bottleneck(nn.Module):
 
     def run(self, x, B, H, W):
         """x: NHWC bf16 [B*H*W, C] -> (out, H', W')   (modified_resnet.py:40-56)."""
-        out = _bn(self.bn1, C_.Conv1x1.apply(x, self.conv1.weight))
+        out, x = C_.Conv1x1Skip.apply(x, self.conv1.weight)        # x: the skip branch, its gradient is added in conv1's dgrad
+        out = _bn(self.bn1, out)
         out = _bn(self.bn2, C_.Conv3x3.apply(out, self.conv2.weight, B, H, W))
         h2, w2 = H, W
         if self.stride > 1:

@@ -156,11 +156,12 @@ def test_attention(cuda_dev, L, H, causal):
 
 
 @pytest.mark.parametrize("B,L,H,causal", [(6, 50, 12, 0), (3, 77, 8, 1), (2, 128, 2, 1), (4, 50, 32, 0), (3, 17, 2, 0),
-                                          (150, 50, 12, 0), (3, 50, 3, 0)])
+                                          (150, 50, 12, 0), (3, 50, 3, 0), (300, 50, 12, 0), (230, 77, 8, 1)])
 def test_attention_tcgen05_core_against_fp32_and_the_mma_core(cuda_dev, B, L, H, causal):
     """The tcgen05 core (default) and the mma.sync core (fallback; also taken for odd head counts at L <= 64) against
     the fp32 restatement, at tile-boundary shapes: two pairs per tile (L <= 64), one pair (L > 64), L = 128 (full
-    tile), more tiles than CTAs (B = 150), and a shape outside the tcgen05 envelope (3 heads at L = 50)."""
+    tile), more tiles than CTAs (B = 150; B = 300 / 230: >= 6 tiles per CTA also for the two-CTAs-per-SM forward), and a
+    shape outside the tcgen05 envelope (3 heads at L = 50)."""
     from declip_b200 import _lib, ops
     torch.manual_seed(11)
     D = H * 64
