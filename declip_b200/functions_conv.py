@@ -1,5 +1,6 @@
 """autograd bridges for the ModifiedResNet image tower (prototype/model/image_encoder/modified_resnet.py) over the
-C ABI.  Activations are NHWC bf16 matrices [B*H*W, C]; convolutions are (im2col +) the tcgen05 GEMM."""
+C ABI.  Activations are NHWC bf16 matrices [B*H*W, C]; 1x1 convolutions are the tcgen05 GEMM, 3x3 convolutions the
+implicit-GEMM kernels of csrc/conv_igemm.cu (im2col + GEMM only for shapes outside their domain and the 3-channel stem)."""
 import ctypes
 
 import os

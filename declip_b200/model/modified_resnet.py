@@ -2,7 +2,8 @@
 constructor, module tree and parameter names (Conv2d / BatchNorm2d / Linear containers so state_dicts and the
 isinstance-based weight-decay grouping carry over), forward signature `forward(x, return_dense=False)`.
 
-Execution: NHWC bf16 activations; 1x1 convs = tcgen05 GEMM, 3x3 convs = im2col + GEMM, BatchNorm2d (+ReLU, +residual)
+Execution: NHWC bf16 activations; 1x1 convs = tcgen05 GEMM, 3x3 convs = implicit GEMM over TMA boxes (csrc/conv_igemm.cu:
+forward, input and weight gradient; no im2col matrix), the block's skip gradient added in conv1's dgrad epilogue, BatchNorm2d (+ReLU, +residual)
 fused apply passes, AvgPool2d(2), AttentionPool2d through the same fused attention core as the transformers
 (32 heads x 64, L = 50).  Only `use_sync_bn=False` is supported — the only mode that runs with the reference's own
 linklink shim (`link.new_group` is missing, `SyncBatchNorm2d` aliases BatchNorm1d)."""
