@@ -99,8 +99,10 @@ class ModifiedResNet(nn.Module):
                  bn_sync_stats=False, use_sync_bn=True):
         super().__init__()
         if use_sync_bn:
-            raise NotImplementedError("declip_b200: use_sync_bn=True does not run in the reference either "
-                                      "(link.new_group is missing from its shim); configs set use_sync_bn: False")
+            raise NotImplementedError("declip_b200: use_sync_bn=True does not run in the reference either (link.new_group is "
+                                      "missing from its shim and its SyncBatchNorm2d aliases BatchNorm1d, SURVEY.md 2.2); set "
+                                      "use_sync_bn: False as experiments/clip_experiments/yfcc15m/yfcc15m_r50_clip does "
+                                      "(yfcc15m_r50_declip and yfcc15m_r50_filip ask for it and need that one-line change)")
         self.output_dim = embed_dim
         self.input_resolution = input_resolution
         self.conv1 = nn.Conv2d(3, width // 2, kernel_size=3, stride=2, padding=1, bias=False)
